@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the cuda_b200 hot path (contract: see DESIGN.md §Measurement).
+
+A *step* is one full greedy contraction of the closed <psi|psi> network of an L=64,
+bond-dim-512, phys-dim-2 MPS (BASELINE.json configs[1]; 128 tensors -> 127 pairwise
+contractions, SURVEY.md 8(d) cfg 2, seed 3, tensors scaled by 1/sqrt(contracted dims)).
+`value` = pairwise contractions per second with inputs resident in HBM; `e2e` = the same
+metric through the public API with HOST (pinned) input buffers, H2D + D2H inside the timed
+region.  `--impl reference` times the reference's own CPU algorithm (numpy backend restated
+in oracle/, all host threads) on the same workload.  N > 1 (torchrun): every rank contracts
+its own independent MPS sample (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_SITES, BOND, PHYS = 64, 512, 2
+
+
+# ----------------------------------------------------------------------------- workload
+def mps_dims(L, D, d):
+  return [1] + [min(D, d**min(i, L - i)) for i in range(1, L)] + [1]
+
+
+def make_kets(L, D, d, seed):
+  rng = np.random.default_rng(seed)
+  dims = mps_dims(L, D, d)
+  return [rng.standard_normal((dims[i], d, dims[i + 1])) / np.sqrt(dims[i] * d) for i in range(L)]
+
+
+def norm_labels(L):
+  labels = []
+  for side in "kb":
+    for i in range(L):
+      labels.append(["e0" if i == 0 else "%s%d" % (side, i), "p%d" % i,
+                     "eL" if i == L - 1 else "%s%d" % (side, i + 1)])
+  return labels
+
+
+def path_and_work(shapes, labels):
+  from tensornetwork_b200 import drivers
+  sizes = {l: s[ax] for s, labs in zip(shapes, labels) for ax, l in enumerate(labs)}
+  path = drivers.greedy_path(labels, [], sizes)
+  # algorithmic work per pairwise step: flops = 2MNK, bytes = (MK + KN + MN) * sizeof
+  labs = [list(l) for l in labels]
+  steps = []
+  for a, b in path:
+    l1, l2 = labs[a], labs[b]
+    sh = [l for l in l1 if l in l2]
+    K = int(np.prod([sizes[l] for l in sh])) if sh else 1
+    M = int(np.prod([sizes[l] for l in l1 if l not in sh] or [1]))
+    N = int(np.prod([sizes[l] for l in l2 if l not in sh] or [1]))
+    steps.append((M, K, N))
+    new = [l for l in l1 if l not in sh] + [l for l in l2 if l not in sh]
+    for i in sorted([a, b], reverse=True):
+      del labs[i]
+    labs.append(new)
+  return path, steps
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+  QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+           "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+           "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index=0):
+    super().__init__(daemon=True)
+    self.gpu = gpu_index
+    self.samples = []
+    self.stop_flag = False
+
+  def run(self):
+    while not self.stop_flag:
+      try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                              "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if len(f) >= 8:
+          self.samples.append(f)
+      except Exception:  # pylint: disable=broad-except
+        pass
+      time.sleep(0.05)
+
+  def summary(self):
+    if not self.samples:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    sm = sorted(float(s[1]) for s in self.samples)
+    reasons = []
+    for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
+                      ("sw_power_cap", 7)):
+      if any(s[col].lower().startswith("active") for s in self.samples):
+        reasons.append(name)
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": reasons,
+            "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+  """The reference's CPU algorithm for the same workload: numpy backend restated in oracle/
+  (tensordot = numpy_backend.py:35-54 -> np.tensordot/OpenBLAS, path = greedy, pairwise loop
+  = path_contractors.py:87-90), with all host threads."""
+  if rank != 0:
+    return
+  from oracle import np_network as nn
+  np_dtype = {"bf16": np.float32, "f32": np.float32, "f64": np.float64}[args.dtype]
+  kets = [k.astype(np_dtype) for k in make_kets(L_SITES, BOND, PHYS, 3)]
+  tensors = kets + [np.conj(k).copy() for k in kets]
+  labels = norm_labels(L_SITES)
+  sizes = {l: t.shape[ax] for t, labs in zip(tensors, labels) for ax, l in enumerate(labs)}
+
+  def step():
+    path = nn.greedy_path(labels, [], sizes)   # the reference searches the path on every call
+    return nn.contract_path(tensors, labels, path, [])
+  for _ in range(args.warmup):
+    step()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    res = step()
+  dt = time.perf_counter() - t0
+  npair = len(tensors) - 1
+  val = npair * args.steps / dt
+  cores = os.cpu_count()
+  line = {
+      "impl": "reference", "metric": "pairwise contractions/s", "value": val, "unit": "contractions/s",
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "f32" if np_dtype == np.float32 else "f64", "data": "synthetic",
+      "config": workload_config(args, 1),
+      "cpu_baseline": {"value": val, "unit": "contractions/s", "cores": cores, "kind": "port",
+                       "sample": "%d full <psi|psi> contractions (127 pairwise each), numpy %s, OpenBLAS threads=all"
+                                 % (args.steps, np.dtype(np_dtype).name)},
+      "e2e": {"value": val, "unit": "contractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "result_check": float(np.real(res)),
+  }
+  print(json.dumps(line))
+
+
+def workload_config(args, world):
+  return {"workload": "cfg2: <psi|psi> of MPS L=%d bond-dim %d phys-dim %d, greedy path, 127 pairwise contractions per network"
+                      % (L_SITES, BOND, PHYS),
+          "networks_per_step_per_gpu": 1, "compute_dtype": args.dtype, "path_provider": "numpy greedy (opt_einsum stand-in)",
+          "parallelism": "replicas x%d (independent MPS samples, no collective)" % world,
+          "l2_policy": "inputs (128 tensors) exceed the 126 MB L2 for f32/f64; bf16 inputs are 134 MB"}
+
+
+# ------------------------------------------------------------------------------ our arm
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="cuda_b200", choices=["cuda_b200", "reference"])
+  ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32", "f64"])
+  ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == "cuda_b200" else max(args.warmup, 1)
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+
+  if args.impl == "reference":
+    run_reference(args, rank, world)
+    return
+
+  import torch
+  import torch.distributed as dist
+  if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+  torch.cuda.set_device(local)
+  import tensornetwork_b200 as tb
+  from tensornetwork_b200 import drivers, _lib
+  be = tb.get_backend()
+  lib = be.lib
+
+  code = {"bf16": _lib.BF16, "f32": _lib.F32, "f64": _lib.F64}[args.dtype]
+  tdtype = {"bf16": torch.bfloat16, "f32": torch.float32, "f64": torch.float64}[args.dtype]
+  esize = {"bf16": 2, "f32": 4, "f64": 8}[args.dtype]
+  kets = make_kets(L_SITES, BOND, PHYS, 3 + rank)
+  host = [torch.from_numpy(np.ascontiguousarray(k)).to(tdtype).pin_memory() for k in kets]
+  host = host + [h.clone().pin_memory() for h in host]           # bra = conj(ket) (real data)
+  labels = norm_labels(L_SITES)
+  shapes = [tuple(h.shape) for h in host]
+  path, work = path_and_work(shapes, labels)
+  npair = len(path)
+  flops_step = sum(2.0 * m * k * n for m, k, n in work)
+  bytes_step = sum((m * k + k * n + m * n) * esize for m, k, n in work)
+  h2d_bytes = sum(h.numel() * esize for h in host)
+
+  dev = [tb.B200Tensor(h.to(be.device), code) for h in host]
+  torch.cuda.synchronize()
+
+  def step_resident():
+    return drivers.contract_network(dev, labels, [], path=path, backend=be)
+
+  def step_e2e():
+    ts = [tb.B200Tensor(h.to(be.device, non_blocking=True), code) for h in host]
+    out = drivers.contract_network(ts, labels, [], path=path, backend=be)
+    return out.t.to("cpu")     # D2H of the scalar result (syncs)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # ---- device-resident timing ------------------------------------------------------
+  for _ in range(args.warmup):
+    res = step_resident()
+  barrier()
+  sampler = ClockSampler(local)
+  sampler.start()
+  l0 = lib.tnb200_launch_count()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(args.steps):
+    res = step_resident()
+  e1.record()
+  barrier()
+  launches = lib.tnb200_launch_count() - l0
+  ms = e0.elapsed_time(e1)
+  sampler.stop_flag = True
+  sampler.join(timeout=2)
+  result_value = float(res.to_host().astype(np.float64))
+
+  # ---- per-launch timing of the dominant kernel (same workload, events around each launch)
+  kern_ms, kern_flops, kern_bytes, kern_name = per_kernel_pass(be, dev, labels, path, work, esize, args)
+
+  # ---- end-to-end timing (host buffers) ----------------------------------------------
+  for _ in range(args.warmup):
+    step_e2e()
+  barrier()
+  t0 = torch.cuda.Event(enable_timing=True)
+  t1 = torch.cuda.Event(enable_timing=True)
+  t0.record()
+  for _ in range(args.steps):
+    out = step_e2e()
+  t1.record()
+  barrier()
+  ms_e2e = t0.elapsed_time(t1)
+
+  if world > 1:
+    tt = torch.tensor([ms, ms_e2e], device=be.device, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(tt[0]), float(tt[1])
+
+  if rank == 0:
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # pylint: disable=broad-except
+      pass
+    if args.dtype == "bf16":
+      peak, peak_src = peaks.get("bf16_tflops", 1590.0), ("measured" if peaks else "fallback")
+      peak_note = "bf16 dense (cuBLAS burst), MEASURED_PEAKS.json" if peaks else "fallback 1.59 PF"
+    elif args.dtype == "f32":
+      peak = peaks.get("bf16_tflops", 1590.0) / 2.0
+      peak_src, peak_note = "derived", "tf32 = measured bf16 / 2 (no measured tf32 figure)"
+    else:
+      peak, peak_src, peak_note = 40.0, "nominal", "B200 FP64 nominal 40 TFLOP/s (no measured fp64 figure)"
+    achieved = kern_flops / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
+    value = world * npair * args.steps / (ms * 1e-3)
+    line = {
+        "metric": "pairwise contractions/s", "value": value, "unit": "contractions/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+        "data": "synthetic", "config": workload_config(args, world),
+        "step_tflops": world * flops_step * args.steps / (ms * 1e-3) / 1e12,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": achieved / peak, "traffic": None, "kernel": kern_name, "peak_source": peak_src,
+                     "peak_note": peak_note,
+                     "note": "dominant kernel family over the 127 launches of one network; "
+                             "achieved = sum(2MNK) / sum(event time per launch)"},
+        "e2e": {"value": world * npair * args.steps / (ms_e2e * 1e-3), "unit": "contractions/s",
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": esize,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "result_check": result_value,
+    }
+    if not args.no_cpu_baseline and world == 1:
+      line["cpu_baseline"] = cpu_baseline(args)
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def per_kernel_pass(be, dev, labels, path, work, esize, args):
+  """Events around every pairwise launch of one network (after warm-up, same stream)."""
+  import torch
+  from tensornetwork_b200 import drivers
+  steps, res_slot = drivers.plan_path([t.shape for t in dev], labels, path, [])
+  reps = max(1, min(args.steps, 5))
+  tot = {}
+  for rep in range(reps + 1):
+    vals = list(dev)
+    evs = []
+    wi = 0
+    for st in steps:
+      if st[0] == "tensordot":
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        vals.append(be.tensordot(vals[st[1]], vals[st[2]], (st[3], st[4])))
+        b.record()
+        name = be.lib.tnb200_last_kernel().decode()
+        evs.append((a, b, name, work[wi]))
+        wi += 1
+      else:
+        vals.append(be.transpose(vals[st[1]], st[2]))
+    torch.cuda.synchronize()
+    if rep == 0:
+      continue  # warm-up replica
+    for a, b, name, (m, k, n) in evs:
+      d = tot.setdefault(name, [0.0, 0.0, 0.0, 0])
+      d[0] += a.elapsed_time(b)
+      d[1] += 2.0 * m * k * n
+      d[2] += (m * k + k * n + m * n) * esize
+      d[3] += 1
+  name = max(tot, key=lambda k: tot[k][1])
+  return tot[name][0], tot[name][1], tot[name][2], name
+
+
+def cpu_baseline(args):
+  """oracle (numpy restatement of the reference numpy backend) on the host cores, bounded sample."""
+  from oracle import np_network as nn
+  np_dtype = np.float64 if args.dtype == "f64" else np.float32
+  kets = [k.astype(np_dtype) for k in make_kets(L_SITES, BOND, PHYS, 3)]
+  tensors = kets + [np.conj(k).copy() for k in kets]
+  labels = norm_labels(L_SITES)
+  sizes = {l: t.shape[ax] for t, labs in zip(tensors, labels) for ax, l in enumerate(labs)}
+  path = nn.greedy_path(labels, [], sizes)
+  nn.contract_path(tensors, labels, path, [])
+  t0 = time.perf_counter()
+  n = args.cpu_baseline_steps
+  for _ in range(n):
+    nn.contract_path(tensors, labels, path, [])
+  dt = time.perf_counter() - t0
+  return {"value": (len(tensors) - 1) * n / dt, "unit": "contractions/s", "cores": os.cpu_count(), "kind": "port",
+          "sample": "%d full networks (127 pairwise each) in numpy %s, all host threads" % (n, np.dtype(np_dtype).name)}
+
+
+if __name__ == "__main__":
+  main()

@@ -1,0 +1,346 @@
+// tensordot.cu — tnb200_tensordot: planner (mode classification, operand repacking, kernel
+// choice) + the generic strided CUDA-core kernel that serves every dtype and every layout.
+//
+// Replaces NumPyBackend.tensordot (backends/numpy/numpy_backend.py:35-54) and the batched
+// matmul of ncon's _batch_cont (ncon_interface.py:280-354).  np.tensordot materialises
+// transposed copies of both operands and calls BLAS; here the operand permutation is folded
+// into the kernel's address computation (SIMT path) or into TMA tensor maps (tcgen05 path).
+#include "gemm.cuh"
+#include <algorithm>
+#include <vector>
+
+namespace tnb {
+
+int copy_strided(const tnb200_tensor_t* src, const tnb200_tensor_t* dst, int conj, cudaStream_t st);
+
+// --------------------------------------------------------------------------- SIMT kernel
+template <typename T>
+struct SimtParams {
+  const T* A; const T* B; T* C;
+  DevModes mB;  // batch modes : s0 = A, s1 = B, s2 = C
+  DevModes mM;  // free A modes: s0 = A, s1 = C
+  DevModes mN;  // free B modes: s0 = B, s1 = C
+  DevModes mK;  // summed modes: s0 = A, s1 = B
+  int64_t M, N, K, batch;
+  int conjA, conjB, a_kfast, b_nfast;
+};
+
+constexpr int SBM = 64, SBN = 64, SBK = 16;
+
+template <typename T, typename Acc>
+__global__ void __launch_bounds__(256) tensordot_simt_kernel(const __grid_constant__ SimtParams<T> p) {
+  __shared__ Acc As[SBK][SBM + 1];
+  __shared__ Acc Bs[SBK][SBN + 1];
+  const int64_t tilesM = (p.M + SBM - 1) / SBM, tilesN = (p.N + SBN - 1) / SBN;
+  int64_t bid = blockIdx.x;
+  const int64_t tn = bid % tilesN; bid /= tilesN;
+  const int64_t tm = bid % tilesM;
+  const int64_t bb = bid / tilesM;
+  int64_t offAb, offBb, offCb;
+  mode_offsets3(p.mB, bb, offAb, offBb, offCb);
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+
+  int am[4], ak[4], bn[4], bk[4];
+  int64_t aoff[4], boff[4];
+  bool aval[4], bval[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int idx = t + 256 * i;
+    if (p.a_kfast) { ak[i] = idx & 15; am[i] = idx >> 4; } else { am[i] = idx & 63; ak[i] = idx >> 6; }
+    if (p.b_nfast) { bn[i] = idx & 63; bk[i] = idx >> 6; } else { bk[i] = idx & 15; bn[i] = idx >> 4; }
+    int64_t m = tm * SBM + am[i], n = tn * SBN + bn[i];
+    aval[i] = m < p.M; bval[i] = n < p.N;
+    aoff[i] = aval[i] ? offAb + mode_offset0(p.mM, m) : 0;
+    boff[i] = bval[i] ? offBb + mode_offset0(p.mN, n) : 0;
+  }
+  Acc acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = acc_zero((Acc*)nullptr);
+
+  for (int64_t k0 = 0; k0 < p.K; k0 += SBK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      Acc v = acc_zero((Acc*)nullptr);
+      int64_t k = k0 + ak[i];
+      if (aval[i] && k < p.K) {
+        int64_t ko, ko1;
+        if (p.mK.n <= 1) ko = k * p.mK.s0[0]; else mode_offsets(p.mK, k, ko, ko1);
+        v = to_acc(p.A[aoff[i] + ko]);
+        if (p.conjA) v = conj_acc(v);
+      }
+      As[ak[i]][am[i]] = v;
+      Acc w = acc_zero((Acc*)nullptr);
+      k = k0 + bk[i];
+      if (bval[i] && k < p.K) {
+        int64_t ko, ko1;
+        if (p.mK.n <= 1) ko1 = k * p.mK.s1[0]; else mode_offsets(p.mK, k, ko, ko1);
+        w = to_acc(p.B[boff[i] + ko1]);
+        if (p.conjB) w = conj_acc(w);
+      }
+      Bs[bk[i]][bn[i]] = w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SBK; ++kk) {
+      Acc a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty + 16 * i]; b[i] = Bs[kk][tx + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) fma_acc(acc[i][j], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int64_t m = tm * SBM + ty + 16 * i;
+    if (m >= p.M) continue;
+    int64_t oa, ocm;
+    mode_offsets(p.mM, m, oa, ocm);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t n = tn * SBN + tx + 16 * j;
+      if (n >= p.N) continue;
+      int64_t ob, ocn;
+      mode_offsets(p.mN, n, ob, ocn);
+      p.C[offCb + ocm + ocn] = FromAcc<T, Acc>::f(acc[i][j]);
+    }
+  }
+}
+
+template <int DT>
+static int launch_simt(const void* A, const void* B, void* C, const ModeList& mB, const ModeList& mM,
+                       const ModeList& mN, const ModeList& mK, bool conjA, bool conjB, cudaStream_t st) {
+  using T = typename DType<DT>::T;
+  using Acc = typename DType<DT>::Acc;
+  SimtParams<T> p;
+  p.A = (const T*)A; p.B = (const T*)B; p.C = (T*)C;
+  if (!to_dev(mB, p.mB) || !to_dev(mM, p.mM) || !to_dev(mN, p.mN) || !to_dev(mK, p.mK)) {
+    set_error("tensordot: more than %d non-mergeable modes in one group", kDevModes);
+    return TNB200_ERR_UNSUPPORTED;
+  }
+  p.M = mM.total(); p.N = mN.total(); p.K = mK.total(); p.batch = mB.total();
+  p.conjA = conjA; p.conjB = conjB;
+  auto last_stride = [](const ModeList& m, int which) -> int64_t {
+    if (m.n == 0) return INT64_MAX;
+    int64_t s = which == 0 ? m.s0[m.n - 1] : m.s1[m.n - 1];
+    return s < 0 ? -s : s;
+  };
+  p.a_kfast = last_stride(mK, 0) <= last_stride(mM, 0);
+  p.b_nfast = last_stride(mN, 0) <= last_stride(mK, 1);
+  int64_t tiles = ((p.M + SBM - 1) / SBM) * ((p.N + SBN - 1) / SBN) * p.batch;
+  TNB_REQUIRE(tiles < (1LL << 31), TNB200_ERR_UNSUPPORTED, "tensordot: output too large for one launch");
+  tensordot_simt_kernel<T, Acc><<<(unsigned)tiles, 256, 0, st>>>(p);
+  TNB_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+}
+
+static int dispatch_simt(int dt, const void* A, const void* B, void* C, const ModeList& mB,
+                         const ModeList& mM, const ModeList& mN, const ModeList& mK, bool cA, bool cB,
+                         cudaStream_t st) {
+  set_kernel_name("simt");
+  switch (dt) {
+    case TNB200_F64: return launch_simt<TNB200_F64>(A, B, C, mB, mM, mN, mK, cA, cB, st);
+    case TNB200_F32: return launch_simt<TNB200_F32>(A, B, C, mB, mM, mN, mK, cA, cB, st);
+    case TNB200_F16: return launch_simt<TNB200_F16>(A, B, C, mB, mM, mN, mK, cA, cB, st);
+    case TNB200_BF16: return launch_simt<TNB200_BF16>(A, B, C, mB, mM, mN, mK, cA, cB, st);
+    case TNB200_C64: return launch_simt<TNB200_C64>(A, B, C, mB, mM, mN, mK, cA, cB, st);
+    case TNB200_C128: return launch_simt<TNB200_C128>(A, B, C, mB, mM, mN, mK, cA, cB, st);
+    case TNB200_I32: return launch_simt<TNB200_I32>(A, B, C, mB, mM, mN, mK, cA, cB, st);
+    case TNB200_I64: return launch_simt<TNB200_I64>(A, B, C, mB, mM, mN, mK, cA, cB, st);
+  }
+  set_error("tensordot: bad dtype %d", dt);
+  return TNB200_ERR_DTYPE;
+}
+
+// ------------------------------------------------------------------------------ planner
+struct KMode { int64_t ext, sa, sb; };
+
+// collapse one operand's view of a mode group to "single stride or not"
+static bool single_mode(const ModeList& in, int which, int64_t& ext, int64_t& stride) {
+  ModeList m;
+  for (int i = 0; i < in.n; ++i) m.push(in.ext[i], which == 0 ? in.s0[i] : (which == 1 ? in.s1[i] : in.s2[i]));
+  merge_modes(m, 1);
+  if (m.n > 1) return false;
+  ext = m.n ? m.ext[0] : 1;
+  stride = m.n ? m.s0[0] : 0;
+  return true;
+}
+
+static ModeList order_k(const ModeList& mK, int by) {
+  std::vector<int> idx(mK.n);
+  for (int i = 0; i < mK.n; ++i) idx[i] = i;
+  std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) {
+    int64_t sx = by == 0 ? mK.s0[x] : mK.s1[x], sy = by == 0 ? mK.s0[y] : mK.s1[y];
+    return llabs(sx) > llabs(sy);
+  });
+  ModeList r;
+  for (int i : idx) r.push(mK.ext[i], mK.s0[i], mK.s1[i]);
+  return r;
+}
+
+// Pack a (batch, free, K) view of one operand into a contiguous row-major [batch, free, K]
+// scratch buffer with the strided-copy kernel (the only place a transpose is materialised).
+static int pack_operand(int dt, const void* src, const ModeList& mB, int wb, const ModeList& mF,
+                        const ModeList& mK, int wk, void** out, cudaStream_t st) {
+  tnb200_tensor_t s, d;
+  s.data = const_cast<void*>(src); s.dtype = dt; d.dtype = dt;
+  int nd = 0;
+  auto add = [&](const ModeList& m, int which) -> bool {
+    for (int i = 0; i < m.n; ++i) {
+      if (nd >= TNB200_MAX_NDIM) return false;
+      s.shape[nd] = m.ext[i];
+      s.stride[nd] = which == 0 ? m.s0[i] : (which == 1 ? m.s1[i] : m.s2[i]);
+      ++nd;
+    }
+    return true;
+  };
+  if (!add(mB, wb) || !add(mF, 0) || !add(mK, wk)) {
+    set_error("tensordot: too many modes to pack");
+    return TNB200_ERR_UNSUPPORTED;
+  }
+  s.ndim = d.ndim = nd;
+  int64_t tot = 1;
+  for (int i = nd - 1; i >= 0; --i) { d.shape[i] = s.shape[i]; d.stride[i] = tot; tot *= s.shape[i]; }
+  int rc = ws_alloc(out, (size_t)tot * dtype_size(dt), st);
+  if (rc) return rc;
+  d.data = *out;
+  return copy_strided(&s, &d, 0, st);
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+
+extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tensor_t* b,
+                                    const tnb200_tensor_t* c, int32_t naxes, const int32_t* axes_a,
+                                    const int32_t* axes_b, int32_t nbatch, const int32_t* batch_a,
+                                    const int32_t* batch_b, int32_t flags, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  TNB_REQUIRE(valid_tensor(a) && valid_tensor(b) && valid_tensor(c), TNB200_ERR_INVALID,
+              "tensordot: invalid tensor descriptor");
+  TNB_REQUIRE(a->dtype == b->dtype && a->dtype == c->dtype, TNB200_ERR_DTYPE,
+              "tensordot: dtype mismatch (%s, %s -> %s)", dtype_name(a->dtype), dtype_name(b->dtype),
+              dtype_name(c->dtype));
+  TNB_REQUIRE(naxes >= 0 && nbatch >= 0 && naxes + nbatch <= a->ndim && naxes + nbatch <= b->ndim,
+              TNB200_ERR_INVALID, "tensordot: too many axes");
+  int role_a[TNB200_MAX_NDIM] = {0}, role_b[TNB200_MAX_NDIM] = {0};  // 0 free, 1 summed, 2 batch
+  ModeList mB, mM, mN, mK;
+  for (int i = 0; i < naxes; ++i) {
+    int x = axes_a[i], y = axes_b[i];
+    if (x < 0) x += a->ndim;
+    if (y < 0) y += b->ndim;
+    TNB_REQUIRE(x >= 0 && x < a->ndim && y >= 0 && y < b->ndim && !role_a[x] && !role_b[y],
+                TNB200_ERR_INVALID, "tensordot: bad or repeated axis");
+    TNB_REQUIRE(a->shape[x] == b->shape[y], TNB200_ERR_INVALID, "shape-mismatch for sum");
+    role_a[x] = 1; role_b[y] = 1;
+    mK.push(a->shape[x], a->stride[x], b->stride[y]);
+  }
+  int cax = 0;
+  for (int i = 0; i < nbatch; ++i) {
+    int x = batch_a[i], y = batch_b[i];
+    if (x < 0) x += a->ndim;
+    if (y < 0) y += b->ndim;
+    TNB_REQUIRE(x >= 0 && x < a->ndim && y >= 0 && y < b->ndim && !role_a[x] && !role_b[y],
+                TNB200_ERR_INVALID, "tensordot: bad or repeated batch axis");
+    TNB_REQUIRE(a->shape[x] == b->shape[y], TNB200_ERR_INVALID, "tensordot: batch extent mismatch");
+    role_a[x] = 2; role_b[y] = 2;
+    TNB_REQUIRE(cax < c->ndim && c->shape[cax] == a->shape[x], TNB200_ERR_INVALID,
+                "tensordot: output shape mismatch (batch axis %d)", i);
+    mB.push(a->shape[x], a->stride[x], b->stride[y], c->stride[cax]);
+    ++cax;
+  }
+  for (int i = 0; i < a->ndim; ++i)
+    if (!role_a[i]) {
+      TNB_REQUIRE(cax < c->ndim && c->shape[cax] == a->shape[i], TNB200_ERR_INVALID,
+                  "tensordot: output shape mismatch at output axis %d", cax);
+      mM.push(a->shape[i], a->stride[i], c->stride[cax]);
+      ++cax;
+    }
+  for (int i = 0; i < b->ndim; ++i)
+    if (!role_b[i]) {
+      TNB_REQUIRE(cax < c->ndim && c->shape[cax] == b->shape[i], TNB200_ERR_INVALID,
+                  "tensordot: output shape mismatch at output axis %d", cax);
+      mN.push(b->shape[i], b->stride[i], c->stride[cax]);
+      ++cax;
+    }
+  TNB_REQUIRE(cax == c->ndim, TNB200_ERR_INVALID, "tensordot: output rank mismatch (%d vs %d)", cax,
+              c->ndim);
+
+  const int dt = a->dtype;
+  const bool conjA = (flags & TNB200_CONJ_A) && dtype_is_complex(dt);
+  const bool conjB = (flags & TNB200_CONJ_B) && dtype_is_complex(dt);
+  const int math = (flags >> 4) & 0xF;
+  const int64_t M = mM.total(), N = mN.total(), K = mK.total(), Bt = mB.total();
+  if (M == 0 || N == 0 || Bt == 0) { set_kernel_name("empty"); return 0; }
+  if (K == 0) { set_kernel_name("fill"); return tnb200_fill(c, 0.0, 0.0, stream); }
+
+  ModeList gB = mB, gM = mM, gN = mN;
+  merge_modes(gB, 3); merge_modes(gM, 2); merge_modes(gN, 2);
+
+  // ---- try the tensor-core / DMMA GEMM paths
+  const bool gemm_dtype = dt == TNB200_F64 || dt == TNB200_F32 || dt == TNB200_F16 || dt == TNB200_BF16;
+  const bool want_gemm = gemm_dtype && math != (TNB200_MATH_SIMT >> 4) &&
+                         !(dt == TNB200_F32 && math == (TNB200_MATH_STRICT >> 4)) &&
+                         (double)M * (double)N * (double)K * (double)Bt >= 32768.0 && gB.n <= 1;
+  if (want_gemm) {
+    int64_t cm_ext, cm_s, cn_ext, cn_s;
+    ModeList cM, cN;
+    for (int i = 0; i < gM.n; ++i) cM.push(gM.ext[i], gM.s1[i]);
+    for (int i = 0; i < gN.n; ++i) cN.push(gN.ext[i], gN.s1[i]);
+    bool c_ok = single_mode(cM, 0, cm_ext, cm_s) && single_mode(cN, 0, cn_ext, cn_s);
+    if (c_ok) {
+      GemmProblem g;
+      g.dtype = dt; g.M = M; g.N = N; g.K = K; g.batch = Bt; g.conjA = conjA; g.conjB = conjB; g.math = math;
+      g.C = c->data; g.c_sm = cm_s; g.c_sn = cn_s; g.c_sb = gB.n ? gB.s2[0] : 0;
+      void *packA = nullptr, *packB = nullptr;
+      // choose a K ordering under which as many operands as possible are plain 2-stride matrices
+      int best = -1, best_score = -1; bool bestA = false, bestB = false;
+      int64_t am_e = 0, am_s = 0, ak_s = 0, bn_e = 0, bn_s = 0, bk_s = 0, tmp_e;
+      for (int cand = 0; cand < 2; ++cand) {
+        ModeList ko = order_k(mK, cand);
+        int64_t e1, s1, e2, s2, e3, s3, e4, s4;
+        bool okA = single_mode(gM, 0, e1, s1) && single_mode(ko, 0, e2, s2);
+        bool okB = single_mode(gN, 0, e3, s3) && single_mode(ko, 1, e4, s4);
+        if (dt != TNB200_F64) {
+          okA = okA && tcgen05_operand_ok(dt, a->data, M, K, s1, s2, gB.n ? gB.s0[0] : 0, Bt);
+          okB = okB && tcgen05_operand_ok(dt, b->data, N, K, s3, s4, gB.n ? gB.s1[0] : 0, Bt);
+        }
+        int score = (okA ? 1 : 0) + (okB ? 1 : 0);
+        if (score > best_score) {
+          best_score = score; best = cand; bestA = okA; bestB = okB;
+          if (okA) { am_e = e1; am_s = s1; ak_s = s2; }
+          if (okB) { bn_e = e3; bn_s = s3; bk_s = s4; }
+        }
+      }
+      (void)am_e; (void)bn_e; (void)tmp_e;
+      ModeList ko = order_k(mK, best);
+      int rc = 0;
+      if (bestA) { g.A = a->data; g.a_sm = am_s; g.a_sk = ak_s; g.a_sb = gB.n ? gB.s0[0] : 0; }
+      else {
+        rc = pack_operand(dt, a->data, gB, 0, gM, ko, 0, &packA, st);
+        g.A = packA; g.a_sm = K; g.a_sk = 1; g.a_sb = M * K;
+      }
+      if (rc == 0) {
+        if (bestB) { g.B = b->data; g.b_sn = bn_s; g.b_sk = bk_s; g.b_sb = gB.n ? gB.s1[0] : 0; }
+        else {
+          ModeList nB;  // free modes of B with B strides in slot 0
+          for (int i = 0; i < gN.n; ++i) nB.push(gN.ext[i], gN.s0[i]);
+          rc = pack_operand(dt, b->data, gB, 1, nB, ko, 1, &packB, st);
+          g.B = packB; g.b_sn = K; g.b_sk = 1; g.b_sb = N * K;
+        }
+      }
+      if (rc == 0) {
+        rc = (dt == TNB200_F64) ? gemm_dmma_f64(g, st) : gemm_tcgen05(g, st);
+      }
+      if (packA) ws_free(packA, st);
+      if (packB) ws_free(packB, st);
+      if (rc != TNB200_ERR_UNSUPPORTED) return rc;
+    }
+  }
+  return dispatch_simt(dt, a->data, b->data, c->data, gB, gM, gN, mK, conjA, conjB, st);
+}

@@ -1,0 +1,368 @@
+"""Host-side contraction / split drivers for the `cuda_b200` backend.
+
+These mirror the reference's *callers* of the backend so the hot
+path can be driven — and benchmarked — on a box where the `tensornetwork` package is not
+installed.  With the package installed the reference's own `tn.ncon`, `contractors.greedy`,
+`split_node*` call the same backend methods and produce the same results.
+
+  ncon(...)             <-> tensornetwork/ncon_interface.py:523-663 (`_jittable_ncon` :364-520)
+  contract_network(...) <-> contractors/opt_einsum_paths/path_contractors.py:36-97 (`base`),
+                            `contract_between` network_components.py:1984-2095
+  split_svd / split_full_svd / split_qr / split_rq
+                        <-> network_operations.py:130-255, 446-588, 258-348, 351-443
+
+Design difference from the reference: the label bookkeeping (pure integer work) is compiled
+once into a *plan* (a flat list of backend calls) keyed by (shapes, labels, orders); executing
+a cached plan is a straight loop of kernel launches with no Python list surgery, which is
+what makes CUDA-graph capture of a whole network possible (graph.py).
+"""
+import numpy as np
+
+_PLAN_CACHE = {}
+
+
+# =============================================================================== ncon
+def _canonicalize(network_structure):
+  """ncon_interface.py:69-115."""
+  flat = [l for sub in network_structure for l in sub]
+  neg_int = sorted({l for l in flat if not isinstance(l, str) and l < 0})
+  pos_int = sorted({l for l in flat if not isinstance(l, str) and l > 0})
+  neg_str = sorted({l for l in flat if isinstance(l, str) and l[0] == '-'}, reverse=True)
+  pos_str = sorted({l for l in flat if isinstance(l, str) and l[0] != '-'})
+  mapping = dict(zip(neg_str + neg_int, range(-len(neg_int + neg_str), 0)))
+  mapping.update(dict(zip(pos_int + pos_str, range(1, 1 + len(pos_int + pos_str)))))
+  return [[mapping[l] for l in labels] for labels in network_structure], mapping
+
+
+def _check_network(net, shapes, con_order, out_order):
+  """The argument checks of ncon_interface.py:118-238 that guard the hot loop."""
+  if len(net) != len(shapes):
+    raise ValueError("len(tensors) != len(network_structure)")
+  for n, (labels, shape) in enumerate(zip(net, shapes)):
+    if len(labels) != len(shape):
+      raise ValueError("number of indices does not match number of labels on tensor {}. "
+                       "len(labels) = {}, len(shape) = {}".format(n, len(labels), len(shape)))
+  sizes = {}
+  for labels, shape in zip(net, shapes):
+    for l, s in zip(labels, shape):
+      if l in sizes and sizes[l] != s:
+        raise ValueError("tensor dimensions for label {} are mismatching: {} != {}".format(
+            l, sizes[l], s))
+      sizes[l] = s
+
+
+def plan_ncon(shapes, network_structure, con_order=None, out_order=None):
+  """Symbolic replay of `_jittable_ncon`: returns (steps, result_slot).
+
+  Each step is a tuple whose first entry names a backend call; operands are slot indices
+  into a growing list of tensors (inputs occupy slots 0..n-1)."""
+  net, mapping = _canonicalize(network_structure)
+  _check_network(net, shapes, con_order, out_order)
+  flat = [l for sub in net for l in sub]
+  uniq = list(set(flat))
+  if not out_order:
+    out_order = sorted([l for l in uniq if l < 0], reverse=True)
+  else:
+    out_order = [mapping[o] for o in out_order]
+  if not con_order:
+    con_order = sorted([l for l in uniq if l > 0])
+  else:
+    con_order = [mapping[o] for o in con_order]
+  init_con_order = list(con_order)
+
+  steps = []
+  nslots = len(shapes)
+  slots = list(range(len(shapes)))       # live tensors (slot ids), parallel to `net`
+  shp = {i: tuple(s) for i, s in enumerate(shapes)}
+
+  def emit(step, shape):
+    nonlocal nslots
+    steps.append(step + (nslots,))
+    shp[nslots] = tuple(shape)
+    nslots += 1
+    return nslots - 1
+
+  # partial traces (ncon_interface.py:241-277)
+  for n in range(len(slots)):
+    labels = net[n]
+    tl = [l for l in labels if labels.count(l) == 2]
+    if tl:
+      num = len(tl) // 2
+      uq = sorted(tl)[0:-1:2]
+      pos = [[i for i, l in enumerate(labels) if l == t] for t in uq]
+      contracted = [p[0] for p in pos] + [p[1] for p in pos]
+      free = [i for i in range(len(labels)) if i not in contracted]
+      s = shp[slots[n]]
+      cdim = int(np.prod([s[d] for d in contracted[:num]]))
+      tmp = tuple([s[p] for p in free] + [cdim, cdim])
+      slots[n] = emit(("ptrace", slots[n], tuple(free + contracted), tmp),
+                      [s[p] for p in free])
+      net[n] = [l for l in labels if l not in uq]
+      con_order = [c for c in con_order if c not in uq]
+
+  flat = [l for sub in net for l in sub]
+  single = [l for l in flat if flat.count(l) == 1 and l > 0]
+  if single:
+    con_order = [o for o in con_order if o not in single]
+  for n, labels in enumerate(net):
+    if set(labels).intersection(single):
+      inds = tuple(labels.index(l) for l in single if l in labels)
+      s = shp[slots[n]]
+      slots[n] = emit(("sum", slots[n], inds), [x for i, x in enumerate(s) if i not in inds])
+      net[n] = [l for l in labels if l not in single]
+
+  batch_labels, batch_cnts = [], []
+  for l in set(flat):
+    cnt = flat.count(l)
+    if cnt > 2 or (cnt == 2 and l < 0):
+      batch_labels.append(l)
+      batch_cnts.append(cnt)
+
+  def batch_cont(s1, s2, l1, l2, cb):
+    """ncon_interface.py:280-354 as ONE batched tensordot (no transposes/reshapes)."""
+    nonlocal con_order
+    cb = list(cb)
+    b1 = [l1.index(l) for l in cb]
+    b2 = [l2.index(l) for l in cb]
+    nb1 = {l for l in l1 if l not in cb}
+    nb2 = {l for l in l2 if l not in cb}
+    cc = list(nb1.intersection(nb2))
+    c1 = [l1.index(l) for l in cc]
+    c2 = [l2.index(l) for l in cc]
+    fp1 = [n for n, l in enumerate(l1) if l not in cc and l not in cb]
+    fp2 = [n for n, l in enumerate(l2) if l not in cc and l not in cb]
+    sh1, sh2 = shp[s1], shp[s2]
+    out_shape = [sh1[i] for i in b1] + [sh1[i] for i in fp1] + [sh2[i] for i in fp2]
+    new = emit(("batched", s1, s2, tuple(c1), tuple(c2), tuple(b1), tuple(b2)), out_shape)
+    slots.append(new)
+    net.append([l1[i] for i in b1] + [l1[i] for i in fp1] + [l2[i] for i in fp2])
+    con_order = [c for c in con_order if c not in cc]
+
+  skip = 0
+  while con_order:
+    ci = con_order[0]
+    if ci in batch_labels:
+      con_order.append(con_order.pop(0))
+      skip += 1
+      if skip > len(con_order):
+        raise ValueError("ncon seems stuck in an infinite loop. \n"
+                         "Please check if `con_order` = {} is a valid contraction order for \n"
+                         "`network_structure` = {}".format(init_con_order, network_structure))
+      continue
+    locs = [n for n, labels in enumerate(net) if ci in labels]
+    s2 = slots.pop(locs[1])
+    s1 = slots.pop(locs[0])
+    l2 = net.pop(locs[1])
+    l1 = net.pop(locs[0])
+    common = list(set(l1).intersection(l2))
+    c1 = [l1.index(l) for l in common]
+    c2 = [l2.index(l) for l in common]
+    cb = set(batch_labels).intersection(common)
+    if cb:
+      delete = []
+      for i, bl in enumerate(batch_labels):
+        if bl in cb:
+          batch_cnts[i] -= 1
+          if (bl > 0 and batch_cnts[i] <= 2) or (bl < 0 and batch_cnts[i] < 2):
+            delete.append(i)
+      for i in sorted(delete, reverse=True):
+        del batch_cnts[i]
+        del batch_labels[i]
+      batch_cont(s1, s2, l1, l2, cb)
+    else:
+      srt = sorted(range(len(c1)), key=lambda i: c1[i])
+      a1 = tuple(c1[i] for i in srt)
+      a2 = tuple(c2[i] for i in srt)
+      sh1, sh2 = shp[s1], shp[s2]
+      out_shape = [x for i, x in enumerate(sh1) if i not in a1] + \
+          [x for i, x in enumerate(sh2) if i not in a2]
+      slots.append(emit(("tensordot", s1, s2, a1, a2), out_shape))
+      net.append([l for l in l1 if l not in common] + [l for l in l2 if l not in common])
+      con_order = [c for c in con_order if c not in common]
+
+  while len(slots) > 1:
+    s2 = slots.pop()
+    s1 = slots.pop()
+    l2 = net.pop()
+    l1 = net.pop()
+    common = list(set(l1).intersection(l2))
+    cb = set(batch_labels).intersection(common)
+    if cb:
+      batch_cont(s1, s2, l1, l2, cb)
+    else:
+      slots.append(emit(("tensordot", s1, s2, (), ()), list(shp[s1]) + list(shp[s2])))
+      net.append(l1 + l2)
+
+  res = slots[0]
+  if len(net[0]) > 1:
+    perm = tuple(net[0].index(l) for l in out_order)
+    if perm != tuple(range(len(perm))):
+      s = shp[res]
+      res = emit(("transpose", res, perm), [s[p] for p in perm])
+  return steps, res
+
+
+def execute_plan(backend, tensors, steps, result_slot):
+  vals = list(tensors)
+  for st in steps:
+    op = st[0]
+    if op == "tensordot":
+      vals.append(backend.tensordot(vals[st[1]], vals[st[2]], (st[3], st[4])))
+    elif op == "batched":
+      vals.append(backend._contract(vals[st[1]], vals[st[2]], list(st[3]), list(st[4]),  # pylint: disable=protected-access
+                                    list(st[5]), list(st[6])))
+    elif op == "ptrace":
+      vals.append(backend.trace(backend.reshape(backend.transpose(vals[st[1]], st[2]), st[3])))
+    elif op == "sum":
+      vals.append(backend.sum(vals[st[1]], st[2]))
+    elif op == "transpose":
+      vals.append(backend.transpose(vals[st[1]], st[2]))
+    else:
+      raise RuntimeError("unknown plan step " + str(op))
+  return vals[result_slot]
+
+
+def ncon(tensors, network_structure, con_order=None, out_order=None, backend=None):
+  """Same call signature / semantics as `tn.ncon` (ncon_interface.py:523) for backend tensors
+  or numpy arrays (converted with `convert_to_tensor`, i.e. copied host->device)."""
+  if backend is None:
+    from .backend import get_instance  # pylint: disable=import-outside-toplevel
+    backend = get_instance()
+  ts = [backend.convert_to_tensor(t) for t in tensors]
+  shapes = tuple(t.shape for t in ts)
+  key = ("ncon", shapes, _freeze(network_structure), _freeze(con_order), _freeze(out_order))
+  plan = _PLAN_CACHE.get(key)
+  if plan is None:
+    plan = plan_ncon(shapes, [list(n) for n in network_structure], con_order, out_order)
+    _PLAN_CACHE[key] = plan
+  return execute_plan(backend, ts, *plan)
+
+
+def _freeze(x):
+  if x is None:
+    return None
+  if isinstance(x, (list, tuple)):
+    return tuple(_freeze(y) for y in x)
+  return x
+
+
+# =================================================================== path contraction
+def greedy_path(labels, out_labels, size_dict, memory_limit=None):
+  """Pairwise order in opt_einsum's convention.  Uses `opt_einsum.paths.greedy` when that
+  package is installed (what `contractors.greedy` calls, path_contractors.py:192), otherwise
+  numpy's own greedy einsum path search, which reproduces the reference's greedy path
+  known-answers (path_calculation_test.py:83-93)."""
+  input_sets = [set(l) for l in labels]
+  try:
+    import opt_einsum  # type: ignore  # pylint: disable=import-outside-toplevel
+    return [tuple(p) for p in opt_einsum.paths.greedy(input_sets, set(out_labels),
+                                                     dict(size_dict), memory_limit)]
+  except ImportError:
+    from numpy._core.einsumfunc import _greedy_path  # pylint: disable=import-outside-toplevel
+    return [tuple(p) for p in _greedy_path(input_sets, set(out_labels), dict(size_dict),
+                                           2**62 if memory_limit is None else memory_limit)]
+
+
+def plan_path(shapes, labels, path, out_labels):
+  """contract_between (network_components.py:2048-2085) replayed symbolically along `path`."""
+  labels = [list(l) for l in labels]
+  slots = list(range(len(shapes)))
+  shp = {i: tuple(s) for i, s in enumerate(shapes)}
+  steps = []
+  nslots = len(shapes)
+  for a, b in path:
+    l1, l2 = labels[a], labels[b]
+    s1, s2 = slots[a], slots[b]
+    shared = [l for l in l1 if l in l2]
+    a1 = [l1.index(l) for l in shared]
+    a2 = [l2.index(l) for l in shared]
+    srt = sorted(range(len(a1)), key=lambda i: a1[i])
+    a1 = tuple(a1[i] for i in srt)
+    a2 = tuple(a2[i] for i in srt)
+    steps.append(("tensordot", s1, s2, a1, a2, nslots))
+    shp[nslots] = tuple([x for i, x in enumerate(shp[s1]) if i not in a1] +
+                        [x for i, x in enumerate(shp[s2]) if i not in a2])
+    new_labels = [l for l in l1 if l not in shared] + [l for l in l2 if l not in shared]
+    for i in sorted([a, b], reverse=True):
+      del labels[i]
+      del slots[i]
+    labels.append(new_labels)
+    slots.append(nslots)
+    nslots += 1
+  res = slots[0]
+  lab = labels[0]
+  if len(lab) > 1:
+    perm = tuple(lab.index(l) for l in out_labels)
+    if perm != tuple(range(len(perm))):
+      steps.append(("transpose", res, perm, nslots))
+      res = nslots
+  return steps, res
+
+
+def contract_network(tensors, labels, out_labels=(), path=None, backend=None,
+                     algorithm=greedy_path):
+  """`contractors.greedy(nodes, output_edge_order)` on (tensor, labels) pairs: every label
+  that appears on two tensors is a connected edge, labels in `out_labels` dangle."""
+  if backend is None:
+    from .backend import get_instance  # pylint: disable=import-outside-toplevel
+    backend = get_instance()
+  ts = [backend.convert_to_tensor(t) for t in tensors]
+  shapes = tuple(t.shape for t in ts)
+  key = ("path", shapes, _freeze(labels), _freeze(out_labels), _freeze(path))
+  plan = _PLAN_CACHE.get(key)
+  if plan is None:
+    if path is None:
+      sizes = {l: s[ax] for s, labs in zip(shapes, labels) for ax, l in enumerate(labs)}
+      path = algorithm(labels, out_labels, sizes)
+    plan = plan_path(shapes, labels, path, list(out_labels))
+    _PLAN_CACHE[key] = plan
+  return execute_plan(backend, ts, *plan)
+
+
+# ============================================================================== split
+def _edge_order(backend, tensor, left_axes, right_axes):
+  order = tuple(left_axes) + tuple(right_axes)
+  if sorted(order) != list(range(tensor.ndim)):
+    raise ValueError("left_axes + right_axes must be a permutation of the tensor's axes")
+  return backend.transpose(tensor, order)
+
+
+def split_svd(tensor, left_axes, right_axes, max_singular_values=None, max_truncation_err=None,
+              relative=False, backend=None):
+  """`tn.split_node` (network_operations.py:130-255): U*sqrt(S), sqrt(S)*Vh, discarded s."""
+  backend = backend or _default()
+  t = _edge_order(backend, backend.convert_to_tensor(tensor), left_axes, right_axes)
+  u, s, vh, trun = backend.svd(t, len(left_axes), max_singular_values, max_truncation_err,
+                               relative=relative)
+  sq = backend.sqrt(s)
+  return (backend.broadcast_right_multiplication(u, sq),
+          backend.broadcast_left_multiplication(sq, vh), trun)
+
+
+def split_full_svd(tensor, left_axes, right_axes, max_singular_values=None,
+                   max_truncation_err=None, relative=False, backend=None):
+  """`tn.split_node_full_svd` (network_operations.py:446-588): U, diagflat(S), Vh, discarded s."""
+  backend = backend or _default()
+  t = _edge_order(backend, backend.convert_to_tensor(tensor), left_axes, right_axes)
+  u, s, vh, trun = backend.svd(t, len(left_axes), max_singular_values, max_truncation_err,
+                               relative=relative)
+  return u, backend.diagflat(s), vh, trun
+
+
+def split_qr(tensor, left_axes, right_axes, backend=None):
+  """`tn.split_node_qr` (network_operations.py:258-348)."""
+  backend = backend or _default()
+  t = _edge_order(backend, backend.convert_to_tensor(tensor), left_axes, right_axes)
+  return backend.qr(t, len(left_axes))
+
+
+def split_rq(tensor, left_axes, right_axes, backend=None):
+  """`tn.split_node_rq` (network_operations.py:351-443)."""
+  backend = backend or _default()
+  t = _edge_order(backend, backend.convert_to_tensor(tensor), left_axes, right_axes)
+  return backend.rq(t, len(left_axes))
+
+
+def _default():
+  from .backend import get_instance  # pylint: disable=import-outside-toplevel
+  return get_instance()

@@ -1,0 +1,138 @@
+"""GPU parity of the drivers (ncon / greedy path / helpers) vs golden vectors + oracle."""
+import numpy as np
+import pytest
+from conftest import load_golden
+from util import assert_close, get_backend
+from oracle import np_backend as nb
+from oracle import np_network as nn
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_ncon():
+  from tensornetwork_b200 import drivers
+  be = get_backend()
+  meta, z = load_golden("ncon")
+  for i, m in enumerate(meta):
+    ts = [z["c%d_t%d" % (i, j)] for j in range(m["n"])]
+    out = drivers.ncon(ts, m["net"], m["con"], m["out"], backend=be)
+    assert_close(out, z["c%d_out" % i], what="ncon case %d" % i)
+
+
+def test_golden_greedy():
+  from tensornetwork_b200 import drivers
+  be = get_backend()
+  meta, z = load_golden("greedy")
+  for ci, m in enumerate(meta):
+    if m.get("open"):
+      ts = [z["open_a"], z["open_b"], z["open_c"]]
+      out, ref = m["out"], z["open_out"]
+    else:
+      kets = [z["c%d_k%d" % (ci, j)] for j in range(m["L"])]
+      ts = kets + [np.conj(k) for k in kets]
+      out, ref = [], z["c%d_out" % ci]
+    res = drivers.contract_network(ts, m["labels"], out, backend=be)
+    assert_close(res, ref, what="greedy case %d" % ci)
+
+
+def test_elementwise_helpers():
+  be = get_backend()
+  rng = np.random.default_rng(11)
+  for dt in ("float64", "float32", "complex128"):
+    x = rng.standard_normal((5, 6, 7)).astype(dt)
+    y = rng.standard_normal((5, 6, 7)).astype(dt)
+    if dt.startswith("complex"):
+      x = x + 1j * rng.standard_normal((5, 6, 7))
+      y = y - 1j * rng.standard_normal((5, 6, 7))
+    X, Y = be.convert_to_tensor(x), be.convert_to_tensor(y)
+    assert_close(be.addition(X, Y), x + y)
+    assert_close(be.subtraction(X, Y), x - y)
+    assert_close(be.multiply(X, Y), x * y)
+    assert_close(be.divide(X, Y), x / y)
+    assert_close(be.conj(X), np.conj(x))
+    assert_close(be.sqrt(be.abs(X)), np.sqrt(np.abs(x)))
+    assert_close(be.exp(X), np.exp(x))
+    assert_close(be.sign(X), np.sign(x))
+    assert_close(be.norm(X), np.asarray(np.linalg.norm(x)))
+    assert_close(be.sum(X, (0, 2)), np.sum(x, axis=(0, 2)))
+    assert_close(be.sum(X, (1,), keepdims=True), np.sum(x, axis=(1,), keepdims=True))
+    assert_close(X * 2.5, x * 2.5)
+    assert_close(3.0 - X, 3.0 - x)
+    assert_close(be.transpose(X, (2, 0, 1)) + be.transpose(Y, (2, 0, 1)), np.transpose(x + y, (2, 0, 1)))
+    v = rng.standard_normal(7).astype(x.real.dtype)
+    assert_close(be.broadcast_right_multiplication(X, be.convert_to_tensor(v)), x * v)
+    w = rng.standard_normal(5).astype(x.real.dtype)
+    assert_close(be.broadcast_left_multiplication(be.convert_to_tensor(w), X), x * w[:, None, None])
+    Z = be.copy(X)
+    Z /= be.norm(X)
+    assert_close(Z, x / np.linalg.norm(x))
+  m = rng.standard_normal((4, 6, 6, 3))
+  M = be.convert_to_tensor(m)
+  assert_close(be.trace(M, axis1=1, axis2=2), np.trace(m, axis1=1, axis2=2))
+  assert_close(be.trace(M, offset=2, axis1=1, axis2=2), np.trace(m, offset=2, axis1=1, axis2=2))
+  assert_close(be.diagflat(be.convert_to_tensor(m[0, 0])), np.diagflat(m[0, 0]))
+  assert_close(be.diagflat(be.convert_to_tensor(m[0, 0, 0]), k=-2), np.diagflat(m[0, 0, 0], k=-2))
+  assert_close(be.diagonal(M, axis1=1, axis2=2), np.diagonal(m, axis1=1, axis2=2))
+  assert_close(be.eye(4, M=6), np.eye(4, M=6))
+  assert_close(be.ones((2, 3), np.float32), np.ones((2, 3), np.float32))
+  assert_close(be.outer_product(be.convert_to_tensor(m[0, 0]), be.convert_to_tensor(m[1, 1])), np.tensordot(m[0, 0], m[1, 1], 0))
+  r = be.randn((256, 256), np.float64, seed=3).to_host()
+  assert abs(r.mean()) < 0.02 and abs(r.std() - 1) < 0.02
+  assert be.reshape(be.transpose(M, (3, 1, 0, 2)), (18, 24)).shape == (18, 24)
+  assert_close(be.reshape(be.transpose(M, (3, 1, 0, 2)), (18, 24)), np.reshape(np.transpose(m, (3, 1, 0, 2)), (18, 24)))
+  with pytest.raises(ValueError):
+    be.broadcast_right_multiplication(M, M)
+
+
+def test_einsum():
+  be = get_backend()
+  rng = np.random.default_rng(12)
+  a, b = rng.standard_normal((3, 4, 5)), rng.standard_normal((4, 3, 6))
+  # numpy_backend_test.py:132-138: 'ij,jil->l'
+  x, y = rng.standard_normal((2, 3)), rng.standard_normal((3, 2, 4))
+  assert_close(be.einsum("ij,jil->l", be.convert_to_tensor(x), be.convert_to_tensor(y)), np.einsum("ij,jil->l", x, y))
+  assert_close(be.einsum("ijk,jil->kl", be.convert_to_tensor(a), be.convert_to_tensor(b)), np.einsum("ijk,jil->kl", a, b))
+  assert_close(be.einsum("ijk,jil->ikl", be.convert_to_tensor(a), be.convert_to_tensor(b)), np.einsum("ijk,jil->ikl", a, b))
+  c = rng.standard_normal((4, 4, 3))
+  assert_close(be.einsum("iij->j", be.convert_to_tensor(c)), np.einsum("iij->j", c))
+  # CopyNode-style (network_components.py:903-908)
+  p, q, r = rng.standard_normal((3, 2)), rng.standard_normal((3, 4)), rng.standard_normal((3, 5))
+  assert_close(be.einsum("ia,ib,ic->abc", *[be.convert_to_tensor(t) for t in (p, q, r)]), np.einsum("ia,ib,ic->abc", p, q, r))
+
+
+def test_lanczos_vs_golden():
+  be = get_backend()
+  meta, z = load_golden("lanczos")
+  for i, m in enumerate(meta):
+    h = be.convert_to_tensor(z["h%d" % i])
+    x0 = be.convert_to_tensor(z["x%d" % i])
+    ev, vecs = be.eigsh_lanczos(lambda x, mat: be.tensordot(mat, x, ([1], [0])), [h], x0,
+                                num_krylov_vecs=m["num_krylov_vecs"], numeig=m["numeig"],
+                                reorthogonalize=m["reorthogonalize"], ndiag=m["ndiag"])
+    np.testing.assert_allclose(ev, z["ev%d" % i], rtol=1e-9, atol=1e-9)
+    for j, v in enumerate(vecs):
+      ref = z["vec%d" % i][j]
+      got = v.to_host()
+      s = np.sign(np.vdot(ref, got))
+      np.testing.assert_allclose(got * s, ref, rtol=0, atol=1e-7)
+
+
+def test_cfg2_mps_norm_small_sizes_and_properties():
+  """<psi|psi> greedy contraction (cfg 2 shape family) vs the oracle at a size the oracle
+  finishes quickly, fp64 <= 1e-10."""
+  from tensornetwork_b200 import drivers
+  be = get_backend()
+  rng = np.random.default_rng(3)
+  L, D, d = 16, 64, 2
+  dims = [1] + [min(D, d**min(i, L - i)) for i in range(1, L)] + [1]
+  kets = [rng.standard_normal((dims[i], d, dims[i + 1])) / np.sqrt(dims[i] * d) for i in range(L)]
+  labels = []
+  for side in "kb":
+    for i in range(L):
+      labels.append(["e0" if i == 0 else "%s%d" % (side, i), "p%d" % i, "eL" if i == L - 1 else "%s%d" % (side, i + 1)])
+  ts = kets + [np.conj(k) for k in kets]
+  sizes = {l: t.shape[ax] for t, labs in zip(ts, labels) for ax, l in enumerate(labs)}
+  path = nn.greedy_path(labels, [], sizes)
+  ref = nn.contract_path(ts, labels, path, [])
+  out = drivers.contract_network(ts, labels, [], path=path, backend=be)
+  assert_close(out, ref, tol=1e-10)

@@ -1,0 +1,120 @@
+"""GPU parity: tnb200_tensordot (through the backend class) vs golden vectors of the real
+reference and vs the numpy oracle on seeded inputs."""
+import numpy as np
+import pytest
+from conftest import load_golden
+from util import assert_close, get_backend, TOL
+from oracle import np_backend as nb
+
+pytestmark = pytest.mark.gpu
+
+
+def test_golden_tensordot():
+  be = get_backend()
+  meta, z = load_golden("tensordot")
+  for i, m in enumerate(meta):
+    a, b = be.convert_to_tensor(z["a%d" % i]), be.convert_to_tensor(z["b%d" % i])
+    if m["perm_a"] is not None:
+      a = be.transpose(a, m["perm_a"])
+    if m["perm_b"] is not None:
+      b = be.transpose(b, m["perm_b"])
+    out = be.tensordot(a, b, m["axes"])
+    assert out.dtype == z["out%d" % i].dtype
+    assert_close(out, z["out%d" % i], what="golden tensordot case %d" % i)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32", "complex128", "complex64", "float16", "int64", "int32"])
+@pytest.mark.parametrize("case", [
+    ((7, 5, 3), (3, 5, 4), ([1, 2], [1, 0])),
+    ((33, 65), (65, 17), ([1], [0])),
+    ((4, 3, 2, 5), (5, 2, 6), ([3, 2], [0, 1])),
+    ((6,), (6,), ([0], [0])),
+    ((3, 4), (5, 6), 0),
+    ((100, 70), (70, 90), 1),
+])
+def test_oracle_random(dtype, case):
+  be = get_backend()
+  sa, sb, axes = case
+  rng = np.random.default_rng(7)
+
+  def mk(shape):
+    if dtype.startswith("int"):
+      return rng.integers(-4, 5, size=shape).astype(dtype)
+    x = rng.standard_normal(shape)
+    if dtype.startswith("complex"):
+      x = x + 1j * rng.standard_normal(shape)
+    return x.astype(dtype)
+  a, b = mk(sa), mk(sb)
+  ref = nb.tensordot(a.astype("float32") if dtype == "float16" else a,
+                     b.astype("float32") if dtype == "float16" else b, axes)
+  out = be.tensordot(be.convert_to_tensor(a), be.convert_to_tensor(b), axes)
+  assert out.shape == ref.shape
+  assert_close(out, ref.astype(dtype) if dtype.startswith("int") else ref, dtype=dtype)
+
+
+def test_strided_views_and_permutes():
+  """transposed / sliced views are consumed in place (fused transpose)."""
+  be = get_backend()
+  rng = np.random.default_rng(8)
+  a = rng.standard_normal((6, 10, 8, 4))
+  b = rng.standard_normal((8, 12, 10))
+  A, B = be.convert_to_tensor(a), be.convert_to_tensor(b)
+  av = be.transpose(A, (3, 1, 0, 2))[1:4]       # shape (3, 10, 6, 8), offset view
+  bv = be.transpose(B, (2, 0, 1))               # (10, 8, 12)
+  ref = np.tensordot(np.transpose(a, (3, 1, 0, 2))[1:4], np.transpose(b, (2, 0, 1)), ([1, 3], [0, 1]))
+  assert_close(be.tensordot(av, bv, ([1, 3], [0, 1])), ref)
+
+
+def test_batched_matmul():
+  """ncon_interface_test.py:472-490 shapes: (10,11,100) x (11,100,12) style batch."""
+  be = get_backend()
+  rng = np.random.default_rng(9)
+  a = rng.standard_normal((5, 7, 11))
+  b = rng.standard_normal((5, 11, 3))
+  assert_close(be.matmul(be.convert_to_tensor(a), be.convert_to_tensor(b)), np.matmul(a, b))
+  a4 = rng.standard_normal((2, 3, 4, 6))
+  b4 = rng.standard_normal((2, 3, 6, 5))
+  assert_close(be.matmul(be.convert_to_tensor(a4), be.convert_to_tensor(b4)), np.matmul(a4, b4))
+  with pytest.raises(ValueError):
+    be.matmul(be.convert_to_tensor(rng.standard_normal(3)), be.convert_to_tensor(rng.standard_normal(3)))
+
+
+def test_errors_match_reference():
+  be = get_backend()
+  a = be.convert_to_tensor(np.ones((2, 3)))
+  b = be.convert_to_tensor(np.ones((4, 5)))
+  with pytest.raises(ValueError):
+    be.tensordot(a, b, ([1], [0]))
+  with pytest.raises(TypeError):
+    be.tensordot(np.ones((2, 3)), b, 0)
+  with pytest.raises(TypeError):
+    be.convert_to_tensor([1, 2, 3])
+
+
+def test_empty_and_scalar_results():
+  be = get_backend()
+  a = be.convert_to_tensor(np.zeros((0, 4)))
+  b = be.convert_to_tensor(np.ones((4, 3)))
+  assert be.tensordot(a, b, ([1], [0])).shape == (0, 3)
+  # numpy_backend_test.py:12-28: ones(2,3,4) . ones(2,3,4) over all axes -> 24.0
+  x = be.convert_to_tensor(2 * np.ones((2, 3, 4)))
+  y = be.convert_to_tensor(np.ones((2, 3, 4)))
+  out = be.tensordot(x, y, ((1, 2), (1, 2)))
+  np.testing.assert_allclose(out.to_host(), np.full((2, 2), 24.0))
+  full = be.tensordot(x, y, ((0, 1, 2), (0, 1, 2)))
+  assert full.shape == () and full.item() == 48.0
+  k0 = be.tensordot(be.convert_to_tensor(np.ones((3, 0))), be.convert_to_tensor(np.ones((0, 2))), 1)
+  np.testing.assert_array_equal(k0.to_host(), np.zeros((3, 2)))
+
+
+@pytest.mark.parametrize("dtype,tolkey", [("float64", "float64"), ("float32", "tf32")])
+@pytest.mark.parametrize("axes", [([2], [0]), ([0], [2]), ([2], [2]), ([0], [0])])
+def test_flagship_two_site_shapes(dtype, tolkey, axes):
+  """SURVEY 8(d) flagship: A,B (512,2,512) over the shared bond, 4 axis variants, full size."""
+  be = get_backend()
+  rng = np.random.default_rng(2)
+  a = (rng.standard_normal((512, 2, 512)) / np.sqrt(512)).astype(dtype)
+  b = (rng.standard_normal((512, 2, 512)) / np.sqrt(512)).astype(dtype)
+  out = be.tensordot(be.convert_to_tensor(a), be.convert_to_tensor(b), axes)
+  ref = np.tensordot(a.astype("float64"), b.astype("float64"), axes)
+  assert_close(out, ref, tol=TOL[tolkey], what="flagship %s %s" % (dtype, axes))
