@@ -173,7 +173,7 @@ inline void merge_modes(ModeList& m, int nops) {
 }
 
 // Device-side compact form (passed by value inside kernel parameter structs).
-constexpr int kDevModes = 8;
+constexpr int kDevModes = 12;
 struct DevModes {
   int n;
   int64_t ext[kDevModes];

@@ -1,0 +1,444 @@
+// gemm_tcgen05.cu — the tensor-core path of tnb200_tensordot for bf16 / f16 / f32(tf32).
+//
+// One persistent, warp-specialised kernel per launch (B200, sm_100a):
+//   warp 0  : TMA producer  — cp.async.bulk.tensor (3-D tiled maps built over the *strided
+//             operand views*, so the tensordot's transpose is performed by the TMA engine),
+//             SWIZZLE_128B tiles into an N-stage shared-memory ring, mbarrier complete_tx.
+//   warp 1  : MMA issuer    — one elected thread issues tcgen05.mma (cta_group::1, M=128,
+//             N=BN<=256, K=32 bytes) from shared-memory descriptors into a TMEM accumulator;
+//             tcgen05.commit releases ring slots / publishes the accumulator.
+//   warp 2  : TMEM allocator (512 columns = two accumulator buffers, so the epilogue of tile i
+//             overlaps the main loop of tile i+1).
+//   warps 4-7: epilogue     — tcgen05.ld (32 lanes x 32 columns per warp), convert, vectorised
+//             stores into the row-major output.
+// Either operand may be K-major (unit stride along the contracted mode) or MN-major (unit
+// stride along the free mode): both are native UMMA layouts, selected in the instruction
+// descriptor — no operand is ever transposed in memory on this path.
+// Ragged edges in M, N, K are handled by TMA out-of-bounds zero fill + predicated stores.
+#include "gemm.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace tnb {
+
+// ------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (visible as a CUDA error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 28); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int KIND>  // 0: f16/bf16 (kind::f16), 1: tf32
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, sm_100 version = 1)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+  d |= (uint64_t)(layout & 7) << 61; // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+
+struct TcParams {
+  int64_t M, N, K, batch;
+  int BN, num_kb, stages, out_kind;   // out_kind: 0 bf16, 1 f16, 2 f32
+  int64_t tiles_m, tiles_n, num_tiles;
+  int a_mn, b_mn;                     // operand is MN-major
+  uint32_t idesc;
+  void* C; int64_t c_sm, c_sb;        // c_sn == 1
+  int vec_ok;
+};
+
+constexpr int kBM = 128;
+constexpr int kRowBytes = 128;        // one swizzle row = BK elements
+constexpr int kThreads = 256;
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ TcParams p) {
+  constexpr int ES = KIND == 0 ? 2 : 4;          // operand element bytes
+  constexpr int BK = kRowBytes / ES;             // 64 (16-bit) or 32 (tf32) elements per k-block
+  constexpr int CHUNK = kRowBytes / ES;          // MN elements per 128-byte row of an MN-major tile
+  constexpr int A_BYTES = kBM * kRowBytes;       // 16 KB per stage
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int BN = p.BN;
+  const int B_BYTES = BN * kRowBytes;
+  const int STAGE_BYTES = A_BYTES + B_BYTES;
+  const int S = p.stages;
+  uint64_t* bars = (uint64_t*)(smem + (size_t)S * STAGE_BYTES);
+  // bars: full[S], empty[S], tmem_full[2], tmem_empty[2]
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = p.num_kb;
+  const int64_t first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer
+    int s = 0; uint32_t ph = 0;
+    for (int64_t tile = first; tile < p.num_tiles; tile += step) {
+      int64_t t = tile;
+      const int ni = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int mi = (int)(t % p.tiles_m);
+      const int bi = (int)(t / p.tiles_m);
+      const int m0 = mi * kBM, n0 = ni * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1);
+        mbar_expect_tx(full_bar(s), (uint32_t)STAGE_BYTES);
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+        const int k0 = kb * BK;
+        if (!p.a_mn) {
+          tma_load_3d(sa, &tmA, full_bar(s), k0, m0, bi);
+        } else {
+#pragma unroll
+          for (int c = 0; c < kBM / CHUNK; ++c)
+            tma_load_3d(sa + c * (BK * kRowBytes), &tmA, full_bar(s), m0 + c * CHUNK, k0, bi);
+        }
+        if (!p.b_mn) {
+          tma_load_3d(sb, &tmB, full_bar(s), k0, n0, bi);
+        } else {
+          for (int c = 0; c < BN / CHUNK; ++c)
+            tma_load_3d(sb + c * (BK * kRowBytes), &tmB, full_bar(s), n0 + c * CHUNK, k0, bi);
+        }
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================================================== MMA issuer
+    // descriptor fields per majorness (see DESIGN.md "UMMA operand layouts")
+    const uint32_t a_layout = (p.a_mn && KIND == 1) ? 1u : 2u;
+    const uint32_t b_layout = (p.b_mn && KIND == 1) ? 1u : 2u;
+    const uint32_t a_lbo = p.a_mn ? BK * kRowBytes : 0u, b_lbo = p.b_mn ? BK * kRowBytes : 0u;
+    const uint32_t a_sbo = (p.a_mn && KIND == 1) ? 512u : 1024u;
+    const uint32_t b_sbo = (p.b_mn && KIND == 1) ? 512u : 1024u;
+    // bytes the start address advances per MMA (K = 32 bytes of the contracted mode)
+    const uint32_t a_kstep = p.a_mn ? (32u / ES) * kRowBytes : 32u;
+    const uint32_t b_kstep = p.b_mn ? (32u / ES) * kRowBytes : 32u;
+    int s = 0; uint32_t ph = 0;
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int64_t tile = first; tile < p.num_tiles; tile += step) {
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, a_layout);
+          const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, b_layout);
+          tc_mma<KIND>(d_tmem, ad, bd, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit(empty_bar(s));                 // frees the ring slot when these MMAs retire
+        if (kb == num_kb - 1) tc_commit(tfull_bar(acc));
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue
+    const int q = warp & 3;                      // TMEM lane quadrant of this warp
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int64_t tile = first; tile < p.num_tiles; tile += step) {
+      int64_t t = tile;
+      const int ni = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int mi = (int)(t % p.tiles_m);
+      const int64_t bi = t / p.tiles_m;
+      const int64_t row = (int64_t)mi * kBM + q * 32 + lane;
+      const int64_t n0 = (int64_t)ni * BN;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        tmem_ld32(taddr0 + j * 32, r);
+        const int64_t col0 = n0 + j * 32;
+        if (row < p.M && col0 < p.N) {
+          const int64_t off = bi * p.c_sb + row * p.c_sm + col0;
+          const int ncol = (p.N - col0) >= 32 ? 32 : (int)(p.N - col0);
+          if (p.out_kind == 2) {
+            float* dst = (float*)p.C + off;
+            if (ncol == 32 && p.vec_ok) {
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                ((float4*)dst)[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                                __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = __uint_as_float(r[c]);
+            }
+          } else {
+            uint16_t* dst = (uint16_t*)p.C + off;
+            uint32_t pk[16];
+#pragma unroll
+            for (int v = 0; v < 16; ++v) {
+              float lo = __uint_as_float(r[2 * v]), hi = __uint_as_float(r[2 * v + 1]);
+              if (p.out_kind == 0) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+                pk[v] = *(uint32_t*)&h;
+              } else {
+                __half2 h = __floats2half2_rn(lo, hi);
+                pk[v] = *(uint32_t*)&h;
+              }
+            }
+            if (ncol == 32 && p.vec_ok) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v) ((uint4*)dst)[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = (uint16_t)(pk[c >> 1] >> ((c & 1) * 16));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+static int es_of(int dt) { return dt == TNB200_F32 ? 4 : 2; }
+
+bool tcgen05_operand_ok(int dtype, const void* ptr, int64_t ext_mn, int64_t ext_k, int64_t s_mn, int64_t s_k,
+                        int64_t s_b, int64_t batch) {
+  if (dtype != TNB200_F32 && dtype != TNB200_F16 && dtype != TNB200_BF16) return false;
+  const int es = es_of(dtype);
+  if (((uintptr_t)ptr) & 15) return false;
+  if (ext_mn >= (1LL << 31) || ext_k >= (1LL << 31) || batch >= (1LL << 31)) return false;
+  auto ok16 = [&](int64_t s) { return s > 0 && (s * es) % 16 == 0 && s * es < (1LL << 40); };
+  if (batch > 1 && !ok16(s_b)) return false;
+  const bool k_unit = (s_k == 1 || ext_k == 1), mn_unit = (s_mn == 1 || ext_mn == 1);
+  if (k_unit && (ext_mn == 1 || ok16(s_mn))) return true;   // K-major
+  if (mn_unit && (ext_k == 1 || ok16(s_k))) {
+    if (dtype == TNB200_F32) {
+      static int tf32_mn = -1;
+      if (tf32_mn < 0) { const char* e = getenv("TNB200_TF32_MN"); tf32_mn = (e && e[0] == '0') ? 0 : 1; }
+      return tf32_mn == 1;
+    }
+    return true;  // MN-major
+  }
+  return false;
+}
+
+static int encode_operand(CUtensorMap* map, int dtype, const void* ptr, int64_t ext_mn, int64_t ext_k, int64_t s_mn,
+                          int64_t s_k, int64_t s_b, int64_t batch, int box_mn, bool& mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return TNB200_ERR_UNSUPPORTED;
+  const int es = es_of(dtype);
+  const int bk = kRowBytes / es, chunk = kRowBytes / es;
+  const bool k_unit = (s_k == 1 || ext_k == 1);
+  const bool k_major = k_unit && (ext_mn == 1 || (s_mn * es) % 16 == 0);
+  mn_major = !k_major;
+  CUtensorMapDataType cdt = dtype == TNB200_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                            : (dtype == TNB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  cuuint64_t dims[3], strides[2];
+  cuuint32_t box[3], estr[3] = {1, 1, 1};
+  // a stride that is never used for addressing (extent 1) still has to be a valid multiple of 16 B
+  auto fix = [&](int64_t s, int64_t fallback_elems) -> cuuint64_t {
+    int64_t b = s * es;
+    if (b <= 0 || b % 16) b = ((fallback_elems * es + 15) / 16) * 16;
+    return (cuuint64_t)b;
+  };
+  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  if (k_major) {
+    dims[0] = (cuuint64_t)ext_k; dims[1] = (cuuint64_t)ext_mn; dims[2] = (cuuint64_t)batch;
+    strides[0] = ext_mn == 1 ? fix(0, ext_k) : (cuuint64_t)(s_mn * es);
+    strides[1] = batch == 1 ? fix(0, ext_k * ext_mn) : (cuuint64_t)(s_b * es);
+    box[0] = bk; box[1] = box_mn; box[2] = 1;
+  } else {
+    dims[0] = (cuuint64_t)ext_mn; dims[1] = (cuuint64_t)ext_k; dims[2] = (cuuint64_t)batch;
+    strides[0] = ext_k == 1 ? fix(0, ext_mn) : (cuuint64_t)(s_k * es);
+    strides[1] = batch == 1 ? fix(0, ext_k * ext_mn) : (cuuint64_t)(s_b * es);
+    box[0] = chunk; box[1] = bk; box[2] = 1;
+    if (dtype == TNB200_F32) sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  }
+  if (strides[1] % 16) strides[1] = ((strides[1] + 15) / 16) * 16;
+  CUresult r = enc(map, cdt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return TNB200_ERR_UNSUPPORTED;
+  return 0;
+}
+
+int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
+  if (g.dtype != TNB200_F32 && g.dtype != TNB200_F16 && g.dtype != TNB200_BF16) return TNB200_ERR_UNSUPPORTED;
+  {
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("TNB200_NO_TCGEN05"); disabled = (e && e[0] == '1') ? 1 : 0; }
+    if (disabled) return TNB200_ERR_UNSUPPORTED;
+  }
+  if (g.conjA || g.conjB) return TNB200_ERR_UNSUPPORTED;
+  if (g.c_sn != 1 && g.N > 1) return TNB200_ERR_UNSUPPORTED;
+  if (g.M >= (1LL << 31) || g.N >= (1LL << 31) || g.K >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
+  if (!tcgen05_operand_ok(g.dtype, g.A, g.M, g.K, g.a_sm, g.a_sk, g.a_sb, g.batch) ||
+      !tcgen05_operand_ok(g.dtype, g.B, g.N, g.K, g.b_sn, g.b_sk, g.b_sb, g.batch))
+    return TNB200_ERR_UNSUPPORTED;
+  const int es = es_of(g.dtype);
+  const int sms = num_sms();
+  const int64_t tiles_m = (g.M + kBM - 1) / kBM;
+  int BN = 64;   // multiples of 64 so that an MN-major B tile is a whole number of 128-byte chunks
+  {
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      int bn = cands[i];
+      if (bn > 64 && bn / 2 >= g.N) continue;          // tile mostly empty
+      int64_t tiles = tiles_m * ((g.N + bn - 1) / bn) * g.batch;
+      if (tiles >= sms || bn == 64) { BN = bn; break; }
+    }
+  }
+  TcParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
+  p.BN = BN;
+  const int bk = kRowBytes / es;
+  p.num_kb = (int)((g.K + bk - 1) / bk);
+  p.tiles_m = tiles_m; p.tiles_n = (g.N + BN - 1) / BN;
+  p.num_tiles = p.tiles_m * p.tiles_n * g.batch;
+  const int stage_bytes = kBM * kRowBytes + BN * kRowBytes;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > p.num_kb + 1 && p.num_tiles <= sms) stages = p.num_kb + 1 > 2 ? p.num_kb + 1 : 2;
+  p.stages = stages;
+  p.out_kind = g.dtype == TNB200_BF16 ? 0 : (g.dtype == TNB200_F16 ? 1 : 2);
+  p.C = g.C; p.c_sm = g.c_sm; p.c_sb = g.c_sb;
+  p.vec_ok = (((uintptr_t)g.C) % 16 == 0) && ((g.c_sm * es) % 16 == 0) && ((g.c_sb * es) % 16 == 0);
+  CUtensorMap tmA, tmB;
+  bool a_mn = false, b_mn = false;
+  int rc = encode_operand(&tmA, g.dtype, g.A, g.M, g.K, g.a_sm, g.a_sk, g.a_sb, g.batch, kBM, a_mn);
+  if (rc) return rc;
+  rc = encode_operand(&tmB, g.dtype, g.B, g.N, g.K, g.b_sn, g.b_sk, g.b_sb, g.batch, BN, b_mn);
+  if (rc) return rc;
+  p.a_mn = a_mn; p.b_mn = b_mn;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B format, majors, N>>3, M>>4
+  const uint32_t fmt = g.dtype == TNB200_BF16 ? 1u : (g.dtype == TNB200_F16 ? 0u : 2u);
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  const int64_t grid = p.num_tiles < sms ? p.num_tiles : sms;
+  static bool attr_set[2] = {false, false};
+  const int kind = g.dtype == TNB200_F32 ? 1 : 0;
+  if (!attr_set[kind]) {
+    cudaError_t e = kind == 0
+        ? cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+        : cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("tcgen05: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return TNB200_ERR_CUDA; }
+    attr_set[kind] = true;
+  }
+  if (kind == 0) gemm_tcgen05_kernel<0><<<(unsigned)grid, kThreads, smem, st>>>(tmA, tmB, p);
+  else gemm_tcgen05_kernel<1><<<(unsigned)grid, kThreads, smem, st>>>(tmA, tmB, p);
+  TNB_LAUNCH_CHECK();
+  count_launch();
+  set_kernel_name(g.dtype == TNB200_BF16 ? "tcgen05_bf16" : (g.dtype == TNB200_F16 ? "tcgen05_f16" : "tcgen05_tf32"));
+  return 0;
+}
+
+}  // namespace tnb

@@ -1,8 +1,6 @@
 #include "gemm.cuh"
 namespace tnb {
-int gemm_tcgen05(const GemmProblem&, cudaStream_t) { return TNB200_ERR_UNSUPPORTED; }
 int gemm_dmma_f64(const GemmProblem&, cudaStream_t) { return TNB200_ERR_UNSUPPORTED; }
-bool tcgen05_operand_ok(int, const void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t) { return false; }
 }
 extern "C" {
 int32_t tnb200_svd(const tnb200_tensor_t*, const tnb200_tensor_t*, const tnb200_tensor_t*, const tnb200_tensor_t*, int32_t*, void*) { tnb::set_error("svd: not built yet"); return TNB200_ERR_UNSUPPORTED; }

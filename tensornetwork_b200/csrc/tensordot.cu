@@ -342,5 +342,7 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
       if (rc != TNB200_ERR_UNSUPPORTED) return rc;
     }
   }
-  return dispatch_simt(dt, a->data, b->data, c->data, gB, gM, gN, mK, conjA, conjB, st);
+  ModeList gK = mK;
+  merge_modes(gK, 2);
+  return dispatch_simt(dt, a->data, b->data, c->data, gB, gM, gN, gK, conjA, conjB, st);
 }

@@ -1,0 +1,86 @@
+"""GPU parity of the tcgen05/TMA tensor-core path (bf16 / f16 / tf32) against float64 numpy on
+identically rounded inputs.  Tolerances: bf16 4e-3 (output rounding 2^-9), f16 1e-3, tf32 1e-3
+(10-bit mantissa inputs, fp32 accumulate), all relative Frobenius."""
+import numpy as np
+import pytest
+from util import assert_close, get_backend, rel_err
+
+pytestmark = pytest.mark.gpu
+TOLS = {"bfloat16": 4e-3, "float16": 1e-3, "float32": 1e-3}
+
+
+def _mk(be, rng, shape, dtype):
+  x = rng.standard_normal(shape).astype(np.float32)
+  if dtype == "float32":
+    t = be.convert_to_tensor(x)
+  else:
+    t = be.astype(be.convert_to_tensor(x), dtype)
+  return t, t.to_host().astype(np.float64)
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16", "float32"])
+@pytest.mark.parametrize("axes", [([2], [0]), ([0], [2]), ([2], [2]), ([0], [0]), ([0, 1], [0, 1]), ([1, 2], [1, 2])])
+def test_two_site_all_majors(dtype, axes):
+  """A,B (256,2,256): every combination of K-major / MN-major operands (fused transposes)."""
+  be = get_backend()
+  rng = np.random.default_rng(21)
+  A, a = _mk(be, rng, (256, 2, 256), dtype)
+  B, b = _mk(be, rng, (256, 2, 256), dtype)
+  out = be.tensordot(A, B, axes)
+  kern = be.lib.tnb200_last_kernel().decode()
+  assert kern.startswith("tcgen05"), kern
+  ref = np.tensordot(a, b, axes)
+  e = rel_err(out.to_host(), ref)
+  assert e < TOLS[dtype], "%s %s via %s: %.3e" % (dtype, axes, kern, e)
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float32"])
+@pytest.mark.parametrize("mkn", [(128, 64, 64), (130, 72, 136), (1000, 520, 264), (64, 1024, 8), (8, 64, 520),
+                                 (512, 512, 1024), (2048, 40, 2048), (136, 8, 72)])
+def test_ragged_sizes(dtype, mkn):
+  be = get_backend()
+  rng = np.random.default_rng(22)
+  m, k, n = mkn
+  A, a = _mk(be, rng, (m, k), dtype)
+  B, b = _mk(be, rng, (k, n), dtype)
+  out = be.tensordot(A, B, 1)
+  kern = be.lib.tnb200_last_kernel().decode()
+  assert rel_err(out.to_host(), a @ b) < TOLS[dtype], (kern, mkn)
+  # transposed operands: (k,m)^T x (n,k)^T
+  At, at = _mk(be, rng, (k, m), dtype)
+  Bt, bt = _mk(be, rng, (n, k), dtype)
+  out2 = be.tensordot(be.transpose(At), be.transpose(Bt), 1)
+  assert rel_err(out2.to_host(), at.T @ bt.T) < TOLS[dtype], (be.lib.tnb200_last_kernel().decode(), mkn)
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float32"])
+def test_batched(dtype):
+  be = get_backend()
+  rng = np.random.default_rng(23)
+  A, a = _mk(be, rng, (6, 256, 128), dtype)
+  B, b = _mk(be, rng, (6, 128, 192), dtype)
+  out = be.matmul(A, B)
+  assert be.lib.tnb200_last_kernel().decode().startswith("tcgen05")
+  assert rel_err(out.to_host(), np.matmul(a, b)) < TOLS[dtype]
+
+
+def test_unaligned_operand_falls_back_to_repack():
+  """odd leading dimension -> not TMA addressable -> repacked, still tensor-core, still right."""
+  be = get_backend()
+  rng = np.random.default_rng(24)
+  A, a = _mk(be, rng, (256, 131), "bfloat16")
+  B, b = _mk(be, rng, (131, 256), "bfloat16")
+  out = be.tensordot(A, B, 1)
+  assert rel_err(out.to_host(), a @ b) < TOLS["bfloat16"]
+
+
+def test_linearity_at_flagship_size():
+  """size-independent property at the flagship shape: T(a1 + a2, b) == T(a1, b) + T(a2, b)."""
+  be = get_backend()
+  rng = np.random.default_rng(25)
+  A1, a1 = _mk(be, rng, (512, 2, 512), "float32")
+  A2, a2 = _mk(be, rng, (512, 2, 512), "float32")
+  B, b = _mk(be, rng, (512, 2, 512), "float32")
+  lhs = be.tensordot(be.addition(A1, A2), B, ([2], [0]))
+  rhs = be.addition(be.tensordot(A1, B, ([2], [0])), be.tensordot(A2, B, ([2], [0])))
+  assert rel_err(lhs.to_host(), rhs.to_host()) < 2e-3
