@@ -1,0 +1,194 @@
+// gemm_dmma.cu — the fp64 path of tnb200_tensordot.
+//
+// tcgen05 has no f64 kind, so double precision runs on the FP64 tensor pipe through
+// mma.sync.aligned.m8n8k4.f64 (DMMA).  B200's FP64 rate is 64 FMA/clk/SM (~40 TFLOP/s), i.e.
+// a 128 x BN x 16 k-block costs >= 2048 cycles of DMMA, which leaves ample room to stage the
+// operands with plain 8-byte cp.async (LDGSTS): the kernel is FP64-pipe bound by construction.
+// Both operands are arbitrary 2-stride matrices (the tensordot's transposes are folded into
+// the cp.async address computation); shared-memory tiles use the majorness of the global
+// operand with a +4-double row pad, which makes every DMMA fragment load conflict-free.
+#include "gemm.cuh"
+
+namespace tnb {
+
+constexpr int DBM = 128, DBK = 16, DSTAGES = 3, DTHREADS = 256;
+
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, bool valid) {
+  int sz = valid ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct DmmaParams {
+  const double* A; const double* B; double* C;
+  int64_t M, N, K, batch;
+  int64_t a_sm, a_sk, a_sb, b_sk, b_sn, b_sb, c_sm, c_sb;
+  int64_t tiles_m, tiles_n;
+  int vec_ok;
+};
+
+// A_K: A tile stored [m][k] (K-major global operand) else [k][m]; B_K likewise ([n][k] / [k][n]).
+template <int BN, bool A_K, bool B_K>
+__global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(const __grid_constant__ DmmaParams p) {
+  constexpr int A_LD = A_K ? DBK + 4 : DBM + 4;
+  constexpr int A_ELEMS = A_K ? DBM * A_LD : DBK * A_LD;
+  constexpr int B_LD = B_K ? DBK + 4 : BN + 4;
+  constexpr int B_ELEMS = B_K ? BN * B_LD : DBK * B_LD;
+  constexpr int WN = BN / 4;          // warp tile: 64 x WN, warps arranged 2 (M) x 4 (N)
+  constexpr int NT = WN / 8;          // n8 tiles per warp
+  extern __shared__ __align__(16) double dsm[];
+  double* As = dsm;
+  double* Bs = dsm + DSTAGES * A_ELEMS;
+
+  int64_t bid = blockIdx.x;
+  const int64_t tn = bid % p.tiles_n; bid /= p.tiles_n;
+  const int64_t tm = bid % p.tiles_m;
+  const int64_t bb = bid / p.tiles_m;
+  const int64_t m0 = tm * DBM, n0 = tn * BN;
+  const double* Ag = p.A + bb * p.a_sb;
+  const double* Bg = p.B + bb * p.b_sb;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = (warp >> 2) * 64, wn = (warp & 3) * WN;
+  const int num_kb = (int)((p.K + DBK - 1) / DBK);
+
+  auto load_stage = [&](int stage, int kb) {
+    const int64_t k0 = (int64_t)kb * DBK;
+    double* as = As + stage * A_ELEMS;
+    double* bs = Bs + stage * B_ELEMS;
+#pragma unroll
+    for (int i = 0; i < DBM * DBK / DTHREADS; ++i) {
+      int idx = tid + i * DTHREADS;
+      int m, k;
+      if (A_K) { k = idx % DBK; m = idx / DBK; } else { m = idx % DBM; k = idx / DBM; }
+      bool ok = (m0 + m < p.M) && (k0 + k < p.K);
+      const double* src = ok ? Ag + (m0 + m) * p.a_sm + (k0 + k) * p.a_sk : Ag;
+      uint32_t dst = (uint32_t)__cvta_generic_to_shared(A_K ? as + m * A_LD + k : as + k * A_LD + m);
+      cp_async8(dst, src, ok);
+    }
+#pragma unroll
+    for (int i = 0; i < BN * DBK / DTHREADS; ++i) {
+      int idx = tid + i * DTHREADS;
+      int n, k;
+      if (B_K) { k = idx % DBK; n = idx / DBK; } else { n = idx % BN; k = idx / BN; }
+      bool ok = (n0 + n < p.N) && (k0 + k < p.K);
+      const double* src = ok ? Bg + (n0 + n) * p.b_sn + (k0 + k) * p.b_sk : Bg;
+      uint32_t dst = (uint32_t)__cvta_generic_to_shared(B_K ? bs + n * B_LD + k : bs + k * B_LD + n);
+      cp_async8(dst, src, ok);
+    }
+  };
+
+  double acc[8][NT][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+#pragma unroll
+  for (int s = 0; s < DSTAGES - 1; ++s) {
+    if (s < num_kb) load_stage(s, s);
+    cp_async_commit();
+  }
+  const int fr = lane >> 2, fk = lane & 3;   // fragment row / k index of this lane
+  for (int kb = 0; kb < num_kb; ++kb) {
+    cp_async_wait<DSTAGES - 2>();
+    __syncthreads();
+    {
+      int nk = kb + DSTAGES - 1;
+      if (nk < num_kb) load_stage(nk % DSTAGES, nk);
+      cp_async_commit();
+    }
+    const double* as = As + (kb % DSTAGES) * A_ELEMS;
+    const double* bs = Bs + (kb % DSTAGES) * B_ELEMS;
+#pragma unroll
+    for (int k4 = 0; k4 < DBK; k4 += 4) {
+      double af[8], bf[NT];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int m = wm + i * 8 + fr, k = k4 + fk;
+        af[i] = A_K ? as[m * A_LD + k] : as[k * A_LD + m];
+      }
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        int n = wn + j * 8 + fr, k = k4 + fk;
+        bf[j] = B_K ? bs[n * B_LD + k] : bs[k * B_LD + n];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+    }
+  }
+  cp_async_wait<0>();
+
+  double* Cg = p.C + bb * p.c_sb;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int64_t m = m0 + wm + i * 8 + fr;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      int64_t n = n0 + wn + j * 8 + 2 * fk;
+      if (n >= p.N) continue;
+      double* dst = Cg + m * p.c_sm + n;
+      if (p.vec_ok && n + 1 < p.N) *(double2*)dst = make_double2(acc[i][j][0], acc[i][j][1]);
+      else { dst[0] = acc[i][j][0]; if (n + 1 < p.N) dst[1] = acc[i][j][1]; }
+    }
+  }
+}
+
+template <int BN, bool A_K, bool B_K>
+static int launch_dmma(const DmmaParams& p, int64_t tiles, cudaStream_t st) {
+  constexpr int A_LD = A_K ? DBK + 4 : DBM + 4;
+  constexpr int A_ELEMS = A_K ? DBM * A_LD : DBK * A_LD;
+  constexpr int B_LD = B_K ? DBK + 4 : BN + 4;
+  constexpr int B_ELEMS = B_K ? BN * B_LD : DBK * B_LD;
+  const size_t smem = (size_t)DSTAGES * (A_ELEMS + B_ELEMS) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_dmma_kernel<BN, A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("dmma: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return TNB200_ERR_CUDA; }
+    attr = true;
+  }
+  gemm_dmma_kernel<BN, A_K, B_K><<<(unsigned)tiles, DTHREADS, smem, st>>>(p);
+  TNB_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+}
+
+int gemm_dmma_f64(const GemmProblem& g, cudaStream_t st) {
+  if (g.dtype != TNB200_F64 || g.conjA || g.conjB) return TNB200_ERR_UNSUPPORTED;
+  if (g.c_sn != 1 && g.N > 1) return TNB200_ERR_UNSUPPORTED;
+  DmmaParams p;
+  p.A = (const double*)g.A; p.B = (const double*)g.B; p.C = (double*)g.C;
+  p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
+  p.a_sm = g.a_sm; p.a_sk = g.a_sk; p.a_sb = g.a_sb;
+  p.b_sk = g.b_sk; p.b_sn = g.b_sn; p.b_sb = g.b_sb;
+  p.c_sm = g.c_sm; p.c_sb = g.c_sb;
+  p.vec_ok = (((uintptr_t)g.C) % 16 == 0) && (g.c_sm % 2 == 0) && (g.c_sb % 2 == 0);
+  p.tiles_m = (g.M + DBM - 1) / DBM;
+  const int sms = num_sms();
+  int BN = 128;
+  if (p.tiles_m * ((g.N + 127) / 128) * g.batch < sms || g.N <= 64) BN = 64;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  const int64_t tiles = p.tiles_m * p.tiles_n * g.batch;
+  if (tiles >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
+  // an operand is loaded "K-major" when its contracted stride is the smaller one
+  const bool a_k = llabs(g.a_sk) <= llabs(g.a_sm) || g.M == 1;
+  const bool b_k = llabs(g.b_sk) <= llabs(g.b_sn) || g.N == 1;
+  set_kernel_name("dmma_f64");
+#define TNB_DMMA(BNV)                                                           \
+  if (a_k && b_k) return launch_dmma<BNV, true, true>(p, tiles, st);            \
+  if (a_k && !b_k) return launch_dmma<BNV, true, false>(p, tiles, st);          \
+  if (!a_k && b_k) return launch_dmma<BNV, false, true>(p, tiles, st);          \
+  return launch_dmma<BNV, false, false>(p, tiles, st);
+  if (BN == 128) { TNB_DMMA(128) } else { TNB_DMMA(64) }
+#undef TNB_DMMA
+}
+
+}  // namespace tnb

@@ -1,0 +1,370 @@
+// svd.cu — tnb200_svd: thin SVD by blocked one-sided (Hestenes) Jacobi, and the truncation
+// count of decompositions.svd (backends/numpy/decompositions.py:21-74; LAPACK gesdd there).
+//
+// The matrix is copied once into column-contiguous working storage W (tall: rows >= cols; a wide
+// input is handled through its transpose).  Columns are grouped in blocks of SB; a sweep visits
+// every block pair in a round-robin tournament (nb-1 rounds of nb/2 disjoint pairs, all pairs of
+// a round processed concurrently):
+//   1. gram   : G = [W_I W_J]^T [W_I W_J]           (2SB x 2SB per pair, split over row chunks)
+//   2. eig    : cyclic Jacobi eigen-decomposition of G in shared memory -> rotation R
+//   3. update : [W_I W_J] <- [W_I W_J] R,  [V_I V_J] <- [V_I V_J] R
+// On convergence (all column pairs orthogonal to tol) sigma_j = |w_j|, U = W / sigma, and the
+// triplets are sorted in descending order by a rank-counting kernel.  R is orthogonal to working
+// precision, so the method is backward stable regardless of how accurately G was formed.
+#include "common.cuh"
+#include <math.h>
+#include <vector>
+
+namespace tnb {
+
+int copy_strided(const tnb200_tensor_t* src, const tnb200_tensor_t* dst, int conj, cudaStream_t st);
+
+constexpr int SB = 16;        // block width
+constexpr int PB = 2 * SB;    // columns handled per pair
+constexpr int RT = 64;        // rows per shared-memory tile
+
+// round-robin tournament on nb (even) players: pair p of round r
+__device__ __forceinline__ void rr_pair(int nb, int r, int p, int& i, int& j) {
+  const int m = nb - 1;
+  if (p == 0) { i = m; j = r % m; }
+  else { i = (r + p) % m; j = (r - p + m) % m; }
+  if (i > j) { int t = i; i = j; j = t; }
+}
+__device__ __forceinline__ int pair_col(int bi, int bj, int c) { return c < SB ? bi * SB + c : bj * SB + (c - SB); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) svd_gram_kernel(const T* __restrict__ W, int64_t R, int nb, int round, T* __restrict__ G, int rsplit) {
+  __shared__ T tile[PB][RT + 1];
+  const int pair = blockIdx.x, chunk = blockIdx.y;
+  int bi, bj;
+  rr_pair(nb, round, pair, bi, bj);
+  const int64_t rows_per = ((R + rsplit - 1) / rsplit + RT - 1) / RT * RT;
+  const int64_t r0 = chunk * rows_per, r1 = min(R, r0 + rows_per);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  T acc[2][2] = {{0, 0}, {0, 0}};
+  for (int64_t rb = r0; rb < r1; rb += RT) {
+    for (int idx = threadIdx.x; idx < PB * RT; idx += 256) {
+      int c = idx / RT, rr = idx % RT;
+      int64_t row = rb + rr;
+      tile[c][rr] = row < r1 ? W[(int64_t)pair_col(bi, bj, c) * R + row] : T(0);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int rr = 0; rr < RT; ++rr) {
+      T a0 = tile[ty * 2][rr], a1 = tile[ty * 2 + 1][rr], b0 = tile[tx * 2][rr], b1 = tile[tx * 2 + 1][rr];
+      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+    }
+    __syncthreads();
+  }
+  T* g = G + (int64_t)pair * PB * PB;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) atomicAdd(&g[(ty * 2 + a) * PB + tx * 2 + b], acc[a][b]);
+}
+
+// Diagonalise the PB x PB Gram matrix of each pair; write the rotation, clear G for the next round,
+// record the largest relative off-diagonal seen BEFORE rotating (sweep convergence measure).
+template <typename T>
+__global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __restrict__ Rout, unsigned int* conv, T tol_inner) {
+  __shared__ T g[PB][PB + 1];
+  __shared__ T rm[PB][PB + 1];
+  __shared__ T cs[SB], sn[SB];
+  __shared__ int pp[SB], qq[SB];
+  __shared__ float red[8];
+  __shared__ float offmax;
+  const int pair = blockIdx.x, tid = threadIdx.x;
+  T* gg = G + (int64_t)pair * PB * PB;
+  for (int idx = tid; idx < PB * PB; idx += 256) {
+    int i = idx / PB, j = idx % PB;
+    g[i][j] = gg[idx];
+    rm[i][j] = i == j ? T(1) : T(0);
+    gg[idx] = T(0);
+  }
+  __syncthreads();
+  for (int sweep = 0; sweep < 10; ++sweep) {
+    // relative off-diagonal measure
+    float loc = 0.f;
+    for (int idx = tid; idx < PB * PB; idx += 256) {
+      int i = idx / PB, j = idx % PB;
+      if (i < j) {
+        T d = g[i][i] * g[j][j];
+        if (d > T(0)) { float v = (float)(fabs((double)g[i][j]) / sqrt((double)d)); loc = fmaxf(loc, v); }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) loc = fmaxf(loc, __shfl_xor_sync(0xffffffffu, loc, o));
+    if ((tid & 31) == 0) red[tid >> 5] = loc;
+    __syncthreads();
+    if (tid == 0) {
+      float m = 0.f;
+      for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]);
+      offmax = m;
+      if (sweep == 0) atomicMax(conv, __float_as_uint(m));
+    }
+    __syncthreads();
+    if (offmax <= (float)tol_inner) break;
+    for (int step = 0; step < PB - 1; ++step) {
+      if (tid < SB) {
+        const int m = PB - 1;
+        int p, q;
+        if (tid == 0) { p = m; q = step % m; } else { p = (step + tid) % m; q = (step - tid + m) % m; }
+        if (p > q) { int t = p; p = q; q = t; }
+        T apq = g[p][q], app = g[p][p], aqq = g[q][q];
+        T c = T(1), s = T(0);
+        if (apq != T(0) && fabs((double)apq) > 1e-300) {
+          T tau = (aqq - app) / (T(2) * apq);
+          T t = (tau >= T(0) ? T(1) : T(-1)) / (fabs(tau) + sqrt(T(1) + tau * tau));
+          c = T(1) / sqrt(T(1) + t * t);
+          s = t * c;
+        }
+        cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
+      }
+      __syncthreads();
+      // column rotations of G and of the accumulated eigenvector matrix
+      for (int idx = tid; idx < SB * PB; idx += 256) {
+        int k = idx / PB, i = idx % PB;
+        T c = cs[k], s = sn[k];
+        int p = pp[k], q = qq[k];
+        T x = g[i][p], y = g[i][q];
+        g[i][p] = c * x - s * y; g[i][q] = s * x + c * y;
+        x = rm[i][p]; y = rm[i][q];
+        rm[i][p] = c * x - s * y; rm[i][q] = s * x + c * y;
+      }
+      __syncthreads();
+      for (int idx = tid; idx < SB * PB; idx += 256) {
+        int k = idx / PB, j = idx % PB;
+        T c = cs[k], s = sn[k];
+        int p = pp[k], q = qq[k];
+        T x = g[p][j], y = g[q][j];
+        g[p][j] = c * x - s * y; g[q][j] = s * x + c * y;
+      }
+      __syncthreads();
+    }
+  }
+  T* ro = Rout + (int64_t)pair * PB * PB;
+  for (int idx = tid; idx < PB * PB; idx += 256) ro[idx] = rm[idx / PB][idx % PB];
+}
+
+// X[:, pair columns] <- X[:, pair columns] * R   (X = W or V; column-contiguous with `rows` rows)
+template <typename T>
+__global__ void __launch_bounds__(256) svd_update_kernel(T* __restrict__ X, int64_t rows, int nb, int round, const T* __restrict__ Rm) {
+  __shared__ T tile[PB][RT + 1];
+  __shared__ T rs[PB][PB + 1];
+  const int pair = blockIdx.x;
+  int bi, bj;
+  rr_pair(nb, round, pair, bi, bj);
+  const T* rg = Rm + (int64_t)pair * PB * PB;
+  for (int idx = threadIdx.x; idx < PB * PB; idx += 256) rs[idx / PB][idx % PB] = rg[idx];
+  const int rr = threadIdx.x & (RT - 1), cg = threadIdx.x / RT;   // 64 rows x 4 column groups of 8
+  for (int64_t rb = (int64_t)blockIdx.y * RT; rb < rows; rb += (int64_t)gridDim.y * RT) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < PB * RT; idx += 256) {
+      int c = idx / RT, r2 = idx % RT;
+      int64_t row = rb + r2;
+      tile[c][r2] = row < rows ? X[(int64_t)pair_col(bi, bj, c) * rows + row] : T(0);
+    }
+    __syncthreads();
+    T out[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[c] = T(0);
+#pragma unroll 8
+    for (int k = 0; k < PB; ++k) {
+      T x = tile[k][rr];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) out[c] += x * rs[k][cg * 8 + c];
+    }
+    int64_t row = rb + rr;
+    if (row < rows) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) X[(int64_t)pair_col(bi, bj, cg * 8 + c) * rows + row] = out[c];
+    }
+  }
+}
+
+template <typename T>
+__global__ void svd_colnorm_kernel(const T* __restrict__ W, int64_t R, int ncols, T* __restrict__ sig) {
+  const int j = blockIdx.x;
+  if (j >= ncols) return;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) { double v = (double)W[(int64_t)j * R + i]; acc += v * v; }
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    sig[j] = (T)sqrt(t);
+  }
+}
+// descending rank by counting (stable: ties keep column order)
+template <typename T>
+__global__ void svd_rank_kernel(const T* __restrict__ sig, int n, int* __restrict__ rank) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  T sj = sig[j];
+  int r = 0;
+  for (int i = 0; i < n; ++i) { T si = sig[i]; r += (si > sj) || (si == sj && i < j); }
+  rank[j] = r;
+}
+// scatter the sorted triplets into the caller's u (m x r), s (r), vh (r x n); `tall` = input had m >= n
+template <typename T>
+__global__ void svd_finalize_kernel(const T* __restrict__ W, const T* __restrict__ V, const T* __restrict__ sig,
+                                    const int* __restrict__ rank, int64_t R, int Cn, int Cp, int r_out, int tall,
+                                    T* __restrict__ u, int64_t u_s0, int64_t u_s1, T* __restrict__ s, int64_t s_s0,
+                                    T* __restrict__ vh, int64_t v_s0, int64_t v_s1) {
+  const int j = blockIdx.x;          // working column
+  const int k = rank[j];
+  if (k >= r_out) return;
+  const T sg = sig[j];
+  const T inv = sg > T(0) ? T(1) / sg : T(0);
+  if (threadIdx.x == 0) s[(int64_t)k * s_s0] = sg;
+  // left factor of the WORK matrix: W[:, j] / sigma (length R); right factor: V[:, j] (length Cn)
+  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) {
+    T val = W[(int64_t)j * R + i] * inv;
+    if (tall) u[i * u_s0 + (int64_t)k * u_s1] = val; else vh[(int64_t)k * v_s0 + i * v_s1] = val;
+  }
+  for (int64_t i = threadIdx.x; i < Cn; i += blockDim.x) {
+    T val = V[(int64_t)j * Cp + i];
+    if (tall) vh[(int64_t)k * v_s0 + i * v_s1] = val; else u[i * u_s0 + (int64_t)k * u_s1] = val;
+  }
+}
+template <typename T>
+__global__ void svd_eye_kernel(T* V, int Cp) {
+  int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx < (int64_t)Cp * Cp) V[idx] = (idx / Cp == idx % Cp) ? T(1) : T(0);
+}
+
+template <typename T>
+static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tnb200_tensor_t* s, const tnb200_tensor_t* vh,
+                    int32_t* info_dev, cudaStream_t st) {
+  const int64_t m = a->shape[0], n = a->shape[1];
+  const bool tall = m >= n;
+  const int64_t R = tall ? m : n;
+  const int Cn = (int)(tall ? n : m);
+  const int Cp = (Cn + PB - 1) / PB * PB;
+  const int nb = Cp / SB, npairs = nb / 2, rounds = nb - 1;
+  if (Cn == 0 || R == 0) return 0;
+  T *W = nullptr, *V = nullptr, *G = nullptr, *Rm = nullptr, *sig = nullptr;
+  int* rank = nullptr;
+  unsigned int* conv = nullptr;
+  int rc;
+  if ((rc = ws_alloc((void**)&W, sizeof(T) * (size_t)Cp * R, st))) return rc;
+  if ((rc = ws_alloc((void**)&V, sizeof(T) * (size_t)Cp * Cp, st))) return rc;
+  if ((rc = ws_alloc((void**)&G, sizeof(T) * (size_t)npairs * PB * PB, st))) return rc;
+  if ((rc = ws_alloc((void**)&Rm, sizeof(T) * (size_t)npairs * PB * PB, st))) return rc;
+  if ((rc = ws_alloc((void**)&sig, sizeof(T) * (size_t)Cp, st))) return rc;
+  if ((rc = ws_alloc((void**)&rank, sizeof(int) * (size_t)Cp, st))) return rc;
+  if ((rc = ws_alloc((void**)&conv, sizeof(unsigned int) * 64, st))) return rc;
+  TNB_CHECK_CUDA(cudaMemsetAsync(W, 0, sizeof(T) * (size_t)Cp * R, st));
+  TNB_CHECK_CUDA(cudaMemsetAsync(G, 0, sizeof(T) * (size_t)npairs * PB * PB, st));
+  // W[j * R + i] = a[i, j] (tall) or a[j, i] (wide)
+  tnb200_tensor_t src = *a, dst;
+  if (!tall) { src.shape[0] = a->shape[1]; src.shape[1] = a->shape[0]; src.stride[0] = a->stride[1]; src.stride[1] = a->stride[0]; }
+  dst.data = W; dst.dtype = a->dtype; dst.ndim = 2;
+  dst.shape[0] = R; dst.shape[1] = Cn; dst.stride[0] = 1; dst.stride[1] = R;
+  if ((rc = copy_strided(&src, &dst, 0, st))) return rc;
+  svd_eye_kernel<T><<<(unsigned)(((int64_t)Cp * Cp + 255) / 256), 256, 0, st>>>(V, Cp);
+  count_launch();
+
+  const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920929e-07;
+  const double tol = 4.0 * sqrt((double)R) * eps;
+  const T tol_inner = (T)(sizeof(T) == 8 ? 1e-15 : 1e-7);
+  int rsplit = (4 * num_sms() + npairs - 1) / npairs;
+  int max_split = (int)((R + 4 * RT - 1) / (4 * RT));
+  if (rsplit > max_split) rsplit = max_split;
+  if (rsplit < 1) rsplit = 1;
+  int usplit_w = (int)((R + RT - 1) / RT); if (usplit_w > rsplit * 4) usplit_w = rsplit * 4;
+  int usplit_v = (Cp + RT - 1) / RT; if (usplit_v > rsplit * 4) usplit_v = rsplit * 4;
+  const int max_sweeps = 40;
+  int sweeps = 0, converged = 0;
+  unsigned int h_conv = 0;
+  for (int sw = 0; sw < max_sweeps; ++sw) {
+    TNB_CHECK_CUDA(cudaMemsetAsync(conv, 0, sizeof(unsigned int), st));
+    for (int r = 0; r < rounds; ++r) {
+      svd_gram_kernel<T><<<dim3(npairs, rsplit), 256, 0, st>>>(W, R, nb, r, G, rsplit);
+      svd_eig_kernel<T><<<npairs, 256, 0, st>>>(G, Rm, conv, tol_inner);
+      svd_update_kernel<T><<<dim3(npairs, usplit_w), 256, 0, st>>>(W, R, nb, r, Rm);
+      svd_update_kernel<T><<<dim3(npairs, usplit_v), 256, 0, st>>>(V, Cp, nb, r, Rm);
+    }
+    count_launch(4 * rounds);
+    TNB_LAUNCH_CHECK();
+    TNB_CHECK_CUDA(cudaMemcpyAsync(&h_conv, conv, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    TNB_CHECK_CUDA(cudaStreamSynchronize(st));
+    ++sweeps;
+    float off;
+    memcpy(&off, &h_conv, 4);
+    if ((double)off <= tol) { converged = 1; break; }
+  }
+  svd_colnorm_kernel<T><<<Cp, 256, 0, st>>>(W, R, Cp, sig);
+  svd_rank_kernel<T><<<(Cp + 255) / 256, 256, 0, st>>>(sig, Cp, rank);
+  svd_finalize_kernel<T><<<Cp, 256, 0, st>>>(W, V, sig, rank, R, Cn, Cp, Cn, tall ? 1 : 0, (T*)u->data, u->stride[0], u->stride[1],
+                                             (T*)s->data, s->stride[0], (T*)vh->data, vh->stride[0], vh->stride[1]);
+  count_launch(3);
+  TNB_LAUNCH_CHECK();
+  if (info_dev) {
+    int32_t h[4] = {sweeps, converged, 0, 0};
+    TNB_CHECK_CUDA(cudaMemcpyAsync(info_dev, h, sizeof(h), cudaMemcpyHostToDevice, st));
+    TNB_CHECK_CUDA(cudaStreamSynchronize(st));
+  }
+  ws_free(W, st); ws_free(V, st); ws_free(G, st); ws_free(Rm, st); ws_free(sig, st); ws_free(rank, st); ws_free(conv, st);
+  if (!converged) { set_error("svd: Jacobi did not converge in %d sweeps", max_sweeps); return TNB200_ERR_NOCONV; }
+  return 0;
+}
+
+// decompositions.py:38-57 on the device, in the arithmetic type of `s` (sequential cumsum like numpy)
+template <typename T>
+__global__ void svd_trunc_kernel(const T* __restrict__ s, int64_t n, int64_t stride, int64_t max_sv, int use_err, double max_err,
+                                 int relative, long long* keep) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long by_err = max_sv;
+  if (use_err) {
+    T eps = relative ? (T)((T)max_err * s[0]) : (T)max_err;
+    T cum = T(0);
+    long long cnt = 0;
+    for (int64_t i = n - 1; i >= 0; --i) {
+      T v = s[i * stride];
+      cum = cum + v * v;
+      if (sqrt(cum) > eps) ++cnt;
+    }
+    by_err = cnt;
+  }
+  *keep = max_sv < by_err ? max_sv : by_err;
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+
+extern "C" int32_t tnb200_svd(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tnb200_tensor_t* s, const tnb200_tensor_t* vh,
+                              int32_t* info_dev, void* stream) {
+  TNB_REQUIRE(valid_tensor(a) && valid_tensor(u) && valid_tensor(s) && valid_tensor(vh), TNB200_ERR_INVALID, "svd: invalid tensor descriptor");
+  TNB_REQUIRE(a->ndim == 2 && u->ndim == 2 && vh->ndim == 2 && s->ndim == 1, TNB200_ERR_INVALID, "svd: expects matrix arguments");
+  const int64_t m = a->shape[0], n = a->shape[1], r = m < n ? m : n;
+  TNB_REQUIRE(u->shape[0] == m && u->shape[1] == r && vh->shape[0] == r && vh->shape[1] == n && s->shape[0] == r, TNB200_ERR_INVALID,
+              "svd: output shapes must be (m,r), (r,), (r,n) with r = min(m,n)");
+  TNB_REQUIRE(u->dtype == a->dtype && vh->dtype == a->dtype, TNB200_ERR_DTYPE, "svd: u/vh dtype must equal the input dtype");
+  TNB_REQUIRE(m < (1LL << 31) && n < (1LL << 31), TNB200_ERR_UNSUPPORTED, "svd: matrix too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  set_kernel_name("svd_block_jacobi");
+  if (a->dtype == TNB200_F64) { TNB_REQUIRE(s->dtype == TNB200_F64, TNB200_ERR_DTYPE, "svd: s must be f64"); return svd_real<double>(a, u, s, vh, info_dev, st); }
+  if (a->dtype == TNB200_F32) { TNB_REQUIRE(s->dtype == TNB200_F32, TNB200_ERR_DTYPE, "svd: s must be f32"); return svd_real<float>(a, u, s, vh, info_dev, st); }
+  set_error("svd: dtype %s is not supported yet (f32/f64 only)", dtype_name(a->dtype));
+  return TNB200_ERR_UNSUPPORTED;
+}
+
+extern "C" int32_t tnb200_svd_truncation_count(const tnb200_tensor_t* s, int64_t max_singular_values, int32_t use_error,
+                                               double max_truncation_error, int32_t relative, int64_t* keep_dev, void* stream) {
+  TNB_REQUIRE(valid_tensor(s) && s->ndim == 1 && keep_dev, TNB200_ERR_INVALID, "svd_truncation_count: invalid arguments");
+  const int64_t n = s->shape[0];
+  int64_t max_sv = max_singular_values < 0 ? n : max_singular_values;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->dtype == TNB200_F64)
+    svd_trunc_kernel<double><<<1, 32, 0, st>>>((const double*)s->data, n, s->stride[0], max_sv, use_error, max_truncation_error, relative, (long long*)keep_dev);
+  else if (s->dtype == TNB200_F32)
+    svd_trunc_kernel<float><<<1, 32, 0, st>>>((const float*)s->data, n, s->stride[0], max_sv, use_error, max_truncation_error, relative, (long long*)keep_dev);
+  else { set_error("svd_truncation_count: s must be f32/f64"); return TNB200_ERR_DTYPE; }
+  TNB_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+}
