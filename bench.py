@@ -113,14 +113,22 @@ def run_reference(args, rank, world):
     return
   from oracle import np_network as nn
   np_dtype = {"bf16": np.float32, "f32": np.float32, "f64": np.float64}[args.dtype]
-  kets = [k.astype(np_dtype) for k in make_kets(L_SITES, BOND, PHYS, 3)]
-  tensors = kets + [np.conj(k).copy() for k in kets]
+  # bounded sample: each reference step contracts `nsamp` of the step's networks (same shapes, same path)
+  nsamp = min(max(1, args.networks), 2)
+  nets = []
+  for b in range(nsamp):
+    kets = [k.astype(np_dtype) for k in make_kets(L_SITES, BOND, PHYS, 3 + b)]
+    nets.append(kets + [np.conj(k).copy() for k in kets])
+  tensors = nets[0]
   labels = norm_labels(L_SITES)
   sizes = {l: t.shape[ax] for t, labs in zip(tensors, labels) for ax, l in enumerate(labs)}
 
   def step():
-    path = nn.greedy_path(labels, [], sizes)   # the reference searches the path on every call
-    return nn.contract_path(tensors, labels, path, [])
+    out = None
+    for ts in nets:
+      path = nn.greedy_path(labels, [], sizes)   # the reference searches the path on every call
+      out = nn.contract_path(ts, labels, path, [])
+    return out
   for _ in range(args.warmup):
     step()
   t0 = time.perf_counter()
@@ -128,7 +136,7 @@ def run_reference(args, rank, world):
     res = step()
   dt = time.perf_counter() - t0
   npair = len(tensors) - 1
-  val = npair * args.steps / dt
+  val = nsamp * npair * args.steps / dt
   cores = os.cpu_count()
   line = {
       "impl": "reference", "metric": "pairwise contractions/s", "value": val, "unit": "contractions/s",
@@ -137,8 +145,8 @@ def run_reference(args, rank, world):
       "dtype": "f32" if np_dtype == np.float32 else "f64", "data": "synthetic",
       "config": workload_config(args, 1),
       "cpu_baseline": {"value": val, "unit": "contractions/s", "cores": cores, "kind": "port",
-                       "sample": "%d full <psi|psi> contractions (127 pairwise each), numpy %s, OpenBLAS threads=all"
-                                 % (args.steps, np.dtype(np_dtype).name)},
+                       "sample": "%d networks per step x %d steps (127 pairwise each), numpy %s, OpenBLAS threads=all"
+                                 % (nsamp, args.steps, np.dtype(np_dtype).name)},
       "e2e": {"value": val, "unit": "contractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "result_check": float(np.real(res)),
   }
@@ -148,7 +156,7 @@ def run_reference(args, rank, world):
 def workload_config(args, world):
   return {"workload": "cfg2: <psi|psi> of MPS L=%d bond-dim %d phys-dim %d, greedy path, 127 pairwise contractions per network"
                       % (L_SITES, BOND, PHYS),
-          "networks_per_step_per_gpu": 1, "compute_dtype": args.dtype, "path_provider": "numpy greedy (opt_einsum stand-in)",
+          "networks_per_step_per_gpu": max(1, args.networks), "launch_mode": "eager" if args.no_graph else "cuda-graph replay", "compute_dtype": args.dtype, "path_provider": "numpy greedy (opt_einsum stand-in)",
           "parallelism": "replicas x%d (independent MPS samples, no collective)" % world,
           "l2_policy": "inputs (128 tensors) exceed the 126 MB L2 for f32/f64; bf16 inputs are 134 MB"}
 
@@ -161,7 +169,10 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="cuda_b200", choices=["cuda_b200", "reference"])
   ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32", "f64"])
-  ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+  ap.add_argument("--networks", type=int, default=8,
+                  help="independent MPS samples contracted in lock-step per step per GPU (batched kernels)")
+  ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
+  ap.add_argument("--cpu-baseline-steps", type=int, default=2)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "cuda_b200" else max(args.warmup, 1)
@@ -186,27 +197,42 @@ def main():
   code = {"bf16": _lib.BF16, "f32": _lib.F32, "f64": _lib.F64}[args.dtype]
   tdtype = {"bf16": torch.bfloat16, "f32": torch.float32, "f64": torch.float64}[args.dtype]
   esize = {"bf16": 2, "f32": 4, "f64": 8}[args.dtype]
-  kets = make_kets(L_SITES, BOND, PHYS, 3 + rank)
-  host = [torch.from_numpy(np.ascontiguousarray(k)).to(tdtype).pin_memory() for k in kets]
+  NB = max(1, args.networks)
+  nbatch = 1 if NB > 1 else 0
+  # NB independent MPS samples per rank (seeds differ per rank and per sample)
+  samples = [make_kets(L_SITES, BOND, PHYS, 3 + 1000 * rank + b) for b in range(NB)]
+  host = []
+  for i in range(L_SITES):
+    arr = np.stack([samples[b][i] for b in range(NB)]) if nbatch else samples[0][i]
+    host.append(torch.from_numpy(np.ascontiguousarray(arr)).to(tdtype).pin_memory())
   host = host + [h.clone().pin_memory() for h in host]           # bra = conj(ket) (real data)
   labels = norm_labels(L_SITES)
-  shapes = [tuple(h.shape) for h in host]
-  path, work = path_and_work(shapes, labels)
+  core_shapes = [tuple(h.shape[nbatch:]) for h in host]
+  path, work = path_and_work(core_shapes, labels)
   npair = len(path)
-  flops_step = sum(2.0 * m * k * n for m, k, n in work)
-  bytes_step = sum((m * k + k * n + m * n) * esize for m, k, n in work)
+  flops_step = NB * sum(2.0 * m * k * n for m, k, n in work)
+  bytes_step = NB * sum((m * k + k * n + m * n) * esize for m, k, n in work)
   h2d_bytes = sum(h.numel() * esize for h in host)
 
+  net = drivers.CompiledNetwork(be, [tuple(h.shape) for h in host], args.dtype if args.dtype != "bf16" else "bfloat16",
+                                labels, [], path=path, nbatch=nbatch) if not args.no_graph else None
   dev = [tb.B200Tensor(h.to(be.device), code) for h in host]
+  if net is not None:
+    net.load(dev)
   torch.cuda.synchronize()
 
   def step_resident():
-    return drivers.contract_network(dev, labels, [], path=path, backend=be)
+    if net is not None:
+      return net()
+    return drivers.contract_network(dev, labels, [], path=path, backend=be, nbatch=nbatch)
 
   def step_e2e():
-    ts = [tb.B200Tensor(h.to(be.device, non_blocking=True), code) for h in host]
-    out = drivers.contract_network(ts, labels, [], path=path, backend=be)
-    return out.t.to("cpu")     # D2H of the scalar result (syncs)
+    if net is not None:
+      out = net(host)           # H2D of every input from pinned host memory, then graph replay
+    else:
+      ts = [tb.B200Tensor(h.to(be.device, non_blocking=True), code) for h in host]
+      out = drivers.contract_network(ts, labels, [], path=path, backend=be, nbatch=nbatch)
+    return out.t.to("cpu")      # D2H of the result (one scalar per network; syncs)
 
   def barrier():
     if world > 1:
@@ -226,14 +252,14 @@ def main():
     res = step_resident()
   e1.record()
   barrier()
-  launches = lib.tnb200_launch_count() - l0
+  launches = (net.launches_per_replay * args.steps) if net is not None else (lib.tnb200_launch_count() - l0)
   ms = e0.elapsed_time(e1)
   sampler.stop_flag = True
   sampler.join(timeout=2)
-  result_value = float(res.to_host().astype(np.float64))
+  result_value = [float(x) for x in np.atleast_1d(res.to_host().astype(np.float64))]
 
-  # ---- per-launch timing of the dominant kernel (same workload, events around each launch)
-  kern_ms, kern_flops, kern_bytes, kern_name = per_kernel_pass(be, dev, labels, path, work, esize, args)
+  # ---- which kernel family carries the flops (one eager replica, names from the library)
+  kern_name, kern_share = dominant_kernel(be, dev, labels, path, work, nbatch)
 
   # ---- end-to-end timing (host buffers) ----------------------------------------------
   for _ in range(args.warmup):
@@ -267,25 +293,29 @@ def main():
       peak_src, peak_note = "derived", "tf32 = measured bf16 / 2 (no measured tf32 figure)"
     else:
       peak, peak_src, peak_note = 40.0, "nominal", "B200 FP64 nominal 40 TFLOP/s (no measured fp64 figure)"
-    achieved = kern_flops / (kern_ms * 1e-3) / 1e12 if kern_ms > 0 else 0.0
-    value = world * npair * args.steps / (ms * 1e-3)
+    # achieved: algorithmic flops of one step / device time of one step (all launches of the step are
+    # back to back in one CUDA graph, so this is flops / (sum of kernel durations + launch gaps))
+    achieved = flops_step * args.steps / (ms * 1e-3) / 1e12
+    value = world * NB * npair * args.steps / (ms * 1e-3)
     line = {
         "metric": "pairwise contractions/s", "value": value, "unit": "contractions/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic", "config": workload_config(args, world),
-        "step_tflops": world * flops_step * args.steps / (ms * 1e-3) / 1e12,
+        "step_tflops": world * achieved,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None, "kernel": kern_name, "peak_source": peak_src,
-                     "peak_note": peak_note,
-                     "note": "dominant kernel family over the 127 launches of one network; "
-                             "achieved = sum(2MNK) / sum(event time per launch)"},
-        "e2e": {"value": world * npair * args.steps / (ms_e2e * 1e-3), "unit": "contractions/s",
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": esize,
+                     "frac": achieved / peak, "traffic": None, "kernel": kern_name, "kernel_flop_share": kern_share,
+                     "peak_source": peak_src, "peak_note": peak_note,
+                     "launches_per_step": launches / args.steps,
+                     "algorithmic_gflop_per_step": flops_step / 1e9, "algorithmic_mb_per_step": bytes_step / 1e6,
+                     "note": "achieved = sum(2MNK over the step's pairwise contractions) / step device time "
+                             "(graph replay: kernel durations + inter-kernel gaps)"},
+        "e2e": {"value": world * NB * npair * args.steps / (ms_e2e * 1e-3), "unit": "contractions/s",
+                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": esize * NB,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "result_check": result_value,
+        "result_check": result_value[:4],
     }
     if not args.no_cpu_baseline and world == 1:
       line["cpu_baseline"] = cpu_baseline(args)
@@ -294,40 +324,29 @@ def main():
     dist.destroy_process_group()
 
 
-def per_kernel_pass(be, dev, labels, path, work, esize, args):
-  """Events around every pairwise launch of one network (after warm-up, same stream)."""
+def dominant_kernel(be, dev, labels, path, work, nbatch):
+  """One eager replica of the step; the library reports which kernel family served each launch."""
   import torch
   from tensornetwork_b200 import drivers
-  steps, res_slot = drivers.plan_path([t.shape for t in dev], labels, path, [])
-  reps = max(1, min(args.steps, 5))
+  steps, _ = drivers.plan_path([t.shape for t in dev], labels, path, [], nbatch)
+  vals = list(dev)
   tot = {}
-  for rep in range(reps + 1):
-    vals = list(dev)
-    evs = []
-    wi = 0
-    for st in steps:
+  wi = 0
+  for st in steps:
+    if st[0] in ("tensordot", "batched"):
       if st[0] == "tensordot":
-        a = torch.cuda.Event(enable_timing=True)
-        b = torch.cuda.Event(enable_timing=True)
-        a.record()
         vals.append(be.tensordot(vals[st[1]], vals[st[2]], (st[3], st[4])))
-        b.record()
-        name = be.lib.tnb200_last_kernel().decode()
-        evs.append((a, b, name, work[wi]))
-        wi += 1
       else:
-        vals.append(be.transpose(vals[st[1]], st[2]))
-    torch.cuda.synchronize()
-    if rep == 0:
-      continue  # warm-up replica
-    for a, b, name, (m, k, n) in evs:
-      d = tot.setdefault(name, [0.0, 0.0, 0.0, 0])
-      d[0] += a.elapsed_time(b)
-      d[1] += 2.0 * m * k * n
-      d[2] += (m * k + k * n + m * n) * esize
-      d[3] += 1
-  name = max(tot, key=lambda k: tot[k][1])
-  return tot[name][0], tot[name][1], tot[name][2], name
+        vals.append(be._contract(vals[st[1]], vals[st[2]], list(st[3]), list(st[4]), list(st[5]), list(st[6])))
+      name = be.lib.tnb200_last_kernel().decode()
+      m, k, n = work[wi]
+      wi += 1
+      tot[name] = tot.get(name, 0.0) + 2.0 * m * k * n
+    else:
+      vals.append(be.transpose(vals[st[1]], st[2]))
+  torch.cuda.synchronize()
+  name = max(tot, key=lambda k: tot[k])
+  return name, tot[name] / sum(tot.values())
 
 
 def cpu_baseline(args):

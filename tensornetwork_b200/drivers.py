@@ -263,8 +263,12 @@ def greedy_path(labels, out_labels, size_dict, memory_limit=None):
                                            2**62 if memory_limit is None else memory_limit)]
 
 
-def plan_path(shapes, labels, path, out_labels):
-  """contract_between (network_components.py:2048-2085) replayed symbolically along `path`."""
+def plan_path(shapes, labels, path, out_labels, nbatch=0):
+  """contract_between (network_components.py:2048-2085) replayed symbolically along `path`.
+
+  nbatch > 0: every tensor carries `nbatch` leading sample axes that are never contracted
+  (independent networks of identical structure, e.g. MPS batch samples, advanced in lock-step by
+  one batched kernel per pairwise step); `labels` describe the remaining axes."""
   labels = [list(l) for l in labels]
   slots = list(range(len(shapes)))
   shp = {i: tuple(s) for i, s in enumerate(shapes)}
@@ -277,11 +281,17 @@ def plan_path(shapes, labels, path, out_labels):
     a1 = [l1.index(l) for l in shared]
     a2 = [l2.index(l) for l in shared]
     srt = sorted(range(len(a1)), key=lambda i: a1[i])
-    a1 = tuple(a1[i] for i in srt)
-    a2 = tuple(a2[i] for i in srt)
-    steps.append(("tensordot", s1, s2, a1, a2, nslots))
-    shp[nslots] = tuple([x for i, x in enumerate(shp[s1]) if i not in a1] +
-                        [x for i, x in enumerate(shp[s2]) if i not in a2])
+    a1 = tuple(a1[i] + nbatch for i in srt)
+    a2 = tuple(a2[i] + nbatch for i in srt)
+    if nbatch:
+      bax = tuple(range(nbatch))
+      steps.append(("batched", s1, s2, a1, a2, bax, bax, nslots))
+      shp[nslots] = tuple(list(shp[s1][:nbatch]) + [x for i, x in enumerate(shp[s1]) if i not in a1 and i >= nbatch] +
+                          [x for i, x in enumerate(shp[s2]) if i not in a2 and i >= nbatch])
+    else:
+      steps.append(("tensordot", s1, s2, a1, a2, nslots))
+      shp[nslots] = tuple([x for i, x in enumerate(shp[s1]) if i not in a1] +
+                          [x for i, x in enumerate(shp[s2]) if i not in a2])
     new_labels = [l for l in l1 if l not in shared] + [l for l in l2 if l not in shared]
     for i in sorted([a, b], reverse=True):
       del labels[i]
@@ -292,15 +302,69 @@ def plan_path(shapes, labels, path, out_labels):
   res = slots[0]
   lab = labels[0]
   if len(lab) > 1:
-    perm = tuple(lab.index(l) for l in out_labels)
+    perm = tuple(range(nbatch)) + tuple(lab.index(l) + nbatch for l in out_labels)
     if perm != tuple(range(len(perm))):
       steps.append(("transpose", res, perm, nslots))
       res = nslots
   return steps, res
 
 
+class CompiledNetwork:
+  """A network contraction frozen into a CUDA graph (the `jit` of this backend).
+
+  The plan's kernel launches — with their TMA descriptors — are captured once on static
+  buffers; each call copies the inputs into those buffers (device->device, or host->device
+  for host inputs) and replays the graph: one driver call instead of one Python round trip
+  per pairwise contraction.  The returned tensor is the graph's static output buffer: it is
+  overwritten by the next call (clone it to keep it)."""
+
+  def __init__(self, backend, shapes, dtype, labels, out_labels=(), path=None, nbatch=0,
+               algorithm=None):
+    from . import tensor as T  # pylint: disable=import-outside-toplevel
+    self.backend = backend
+    self.nbatch = nbatch
+    torch = backend.torch
+    code = T.dtype_code(dtype)
+    core_shapes = [tuple(s[nbatch:]) for s in shapes]
+    if path is None:
+      sizes = {l: s[ax] for s, labs in zip(core_shapes, labels) for ax, l in enumerate(labs)}
+      path = (algorithm or greedy_path)(labels, out_labels, sizes)
+    self.path = path
+    self.steps, self.res_slot = plan_path([tuple(s) for s in shapes], labels, path,
+                                          list(out_labels), nbatch)
+    self.inputs = [backend._new(s, code) for s in shapes]  # pylint: disable=protected-access
+    for t in self.inputs:
+      backend.lib.tnb200_fill(t.ref(), 0.0, 0.0, backend._stream())  # pylint: disable=protected-access
+    self.num_pairwise = len(path)
+    # warm-up on a side stream (loads kernels, sets function attributes), then capture
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      execute_plan(backend, self.inputs, self.steps, self.res_slot)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    self.graph = torch.cuda.CUDAGraph()
+    l0 = backend.lib.tnb200_launch_count()
+    with torch.cuda.graph(self.graph):
+      self.output = execute_plan(backend, self.inputs, self.steps, self.res_slot)
+    self.launches_per_replay = int(backend.lib.tnb200_launch_count() - l0)
+
+  def load(self, tensors):
+    """copy inputs (B200Tensor, torch tensors or pinned host tensors) into the static buffers"""
+    from .tensor import B200Tensor  # pylint: disable=import-outside-toplevel
+    for dst, src in zip(self.inputs, tensors):
+      t = src.t if isinstance(src, B200Tensor) else src
+      dst.t.copy_(t, non_blocking=True)
+
+  def __call__(self, tensors=None):
+    if tensors is not None:
+      self.load(tensors)
+    self.graph.replay()
+    return self.output
+
+
 def contract_network(tensors, labels, out_labels=(), path=None, backend=None,
-                     algorithm=greedy_path):
+                     algorithm=greedy_path, nbatch=0):
   """`contractors.greedy(nodes, output_edge_order)` on (tensor, labels) pairs: every label
   that appears on two tensors is a connected edge, labels in `out_labels` dangle."""
   if backend is None:
@@ -308,13 +372,13 @@ def contract_network(tensors, labels, out_labels=(), path=None, backend=None,
     backend = get_instance()
   ts = [backend.convert_to_tensor(t) for t in tensors]
   shapes = tuple(t.shape for t in ts)
-  key = ("path", shapes, _freeze(labels), _freeze(out_labels), _freeze(path))
+  key = ("path", shapes, _freeze(labels), _freeze(out_labels), _freeze(path), nbatch)
   plan = _PLAN_CACHE.get(key)
   if plan is None:
     if path is None:
-      sizes = {l: s[ax] for s, labs in zip(shapes, labels) for ax, l in enumerate(labs)}
+      sizes = {l: s[nbatch + ax] for s, labs in zip(shapes, labels) for ax, l in enumerate(labs)}
       path = algorithm(labels, out_labels, sizes)
-    plan = plan_path(shapes, labels, path, list(out_labels))
+    plan = plan_path(shapes, labels, path, list(out_labels), nbatch)
     _PLAN_CACHE[key] = plan
   return execute_plan(backend, ts, *plan)
 

@@ -20,7 +20,10 @@ def test_golden_tensordot():
       b = be.transpose(b, m["perm_b"])
     out = be.tensordot(a, b, m["axes"])
     assert out.dtype == z["out%d" % i].dtype
-    assert_close(out, z["out%d" % i], what="golden tensordot case %d" % i)
+    kern = be.lib.tnb200_last_kernel().decode()
+    # float32 on the tensor cores is TF32 (10-bit mantissa): stated tolerance 2e-3
+    tol = TOL["tf32"] if kern.startswith("tcgen05") else None
+    assert_close(out, z["out%d" % i], tol=tol, what="golden tensordot case %d via %s" % (i, kern))
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32", "complex128", "complex64", "float16", "int64", "int32"])
@@ -118,3 +121,20 @@ def test_flagship_two_site_shapes(dtype, tolkey, axes):
   out = be.tensordot(be.convert_to_tensor(a), be.convert_to_tensor(b), axes)
   ref = np.tensordot(a.astype("float64"), b.astype("float64"), axes)
   assert_close(out, ref, tol=TOL[tolkey], what="flagship %s %s" % (dtype, axes))
+
+
+def test_strict_fp32_mode_is_true_fp32():
+  """TNB200_MATH_STRICT: float32 never drops to TF32 (CUDA-core fp32 FMA kernel), tol 2e-5."""
+  from tensornetwork_b200 import _lib as L
+  be = get_backend()
+  rng = np.random.default_rng(5)
+  a = rng.standard_normal((256, 2, 256)).astype(np.float32)
+  b = rng.standard_normal((256, 2, 256)).astype(np.float32)
+  old = be.math_mode
+  try:
+    be.math_mode = L.MATH_STRICT
+    out = be.tensordot(be.convert_to_tensor(a), be.convert_to_tensor(b), ([2], [0]))
+    assert be.lib.tnb200_last_kernel().decode() == "simt"
+  finally:
+    be.math_mode = old
+  assert_close(out, np.tensordot(a.astype(np.float64), b.astype(np.float64), ([2], [0])), tol=2e-5)

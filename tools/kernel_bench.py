@@ -1,0 +1,59 @@
+"""Kernel-level throughput probe (GPU box only): times N back-to-back launches of one tensordot
+shape with CUDA events, so that the host round trip is amortised.  Prints one JSON line per case."""
+import json
+import sys
+import os
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import tensornetwork_b200 as tb
+
+
+def run(be, dtype, shape_a, shape_b, axes, reps=50, batch=None):
+  rng = np.random.default_rng(0)
+  tdt = {"bf16": torch.bfloat16, "f32": torch.float32, "f64": torch.float64, "f16": torch.float16}[dtype]
+  a = tb.B200Tensor(torch.randn(shape_a, device=be.device, dtype=torch.float32).to(tdt))
+  b = tb.B200Tensor(torch.randn(shape_b, device=be.device, dtype=torch.float32).to(tdt))
+  if batch:
+    f = lambda: be.matmul(a, b)
+  else:
+    f = lambda: be.tensordot(a, b, axes)
+  for _ in range(3):
+    out = f()
+  torch.cuda.synchronize()
+  g = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(g):
+    for _ in range(reps):
+      out = f()
+  kern = be.lib.tnb200_last_kernel().decode()
+  g.replay()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  g.replay()
+  e1.record()
+  torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / reps
+  sa, sb = a.shape, b.shape
+  if batch:
+    flops = 2.0 * np.prod(sa) * sb[-1]
+  else:
+    ka = [sa[i] for i in axes[0]]
+    flops = 2.0 * np.prod(sa) * np.prod(sb) / np.prod(ka)
+  es = {"bf16": 2, "f16": 2, "f32": 4, "f64": 8}[dtype]
+  byts = (np.prod(sa) + np.prod(sb) + out.size) * es
+  print(json.dumps({"dtype": dtype, "a": list(sa), "b": list(sb), "axes": axes if not batch else "matmul", "kernel": kern,
+                    "us": ms * 1e3, "tflops": flops / ms / 1e9, "gbs": byts / ms / 1e6}))
+
+
+if __name__ == "__main__":
+  be = tb.get_backend()
+  for dt in ("bf16", "f32", "f64"):
+    run(be, dt, (512, 2, 512), (512, 2, 512), [[2], [0]])
+    run(be, dt, (512, 2, 512), (512, 2, 512), [[0], [2]])
+    run(be, dt, (1024, 512), (512, 512), [[1], [0]])
+    run(be, dt, (4096, 4096), (4096, 4096), [[1], [0]], reps=10)
+    run(be, dt, (4096, 4096), (4096, 4096), [[0], [1]], reps=10)
+    run(be, dt, (8192, 1024), (1024, 8192), [[1], [0]], reps=10)
+    run(be, dt, (64, 1024, 512), (64, 512, 1024), None, reps=10, batch=True)
+    run(be, dt, (256, 1024, 512), (256, 512, 1024), None, reps=5, batch=True)
