@@ -1,0 +1,296 @@
+"""Abelian-symmetric (U(1) / Z_N) block-sparse tensors on the `cuda_b200` backend.
+
+Covers SURVEY.md 8(a) row a11: `block_sparse.tensordot`
+(tensornetwork/block_sparse/blocksparsetensor.py:925-1108) with its index maps
+(blocksparse_utils.py:330-634) and charge fusion (charge.py:21-673).
+
+Storage convention = the reference's: `data` is a flat vector holding, in row-major order of
+the *stored* leg order, exactly those elements of the dense tensor whose fused charge
+sum_i s_i * q_i is the identity (s_i = -1 for an outflowing leg (flow True), +1 otherwise,
+charge.py:622 `fuse_charges`); transposition only permutes the logical `order`
+(blocksparsetensor.py:803-860 makes it contiguous on demand).
+
+The reference executes tensordot as a Python loop over charge sectors of
+gather -> np.matmul -> scatter (:1094-1101).  Here the int64 gather/scatter maps are built once
+per (charges, flows, order, partition) signature on the host (pure integer work, cached, and
+checked bit-exactly against the reference's maps in tests/) and ALL sectors run in ONE launch
+of the grouped kernel `tnb200_blocksparse_tensordot`.
+"""
+import numpy as np
+from . import _lib as L
+from . import tensor as T
+from .tensor import B200Tensor
+
+_MAP_CACHE = {}
+
+
+class Index:
+  """One tensor leg: an integer charge per basis state and a flow (True = outflowing), the
+  information content of `block_sparse.Index` (index.py) for a single Abelian symmetry."""
+
+  def __init__(self, charges, flow, modulus=None):
+    self.charges = np.asarray(charges, dtype=np.int64).ravel()
+    self.flow = bool(flow)
+    self.modulus = modulus  # None: U(1); N: Z_N
+
+  @property
+  def dim(self):
+    return int(self.charges.shape[0])
+
+  def flip_flow(self):
+    return Index(self.charges, not self.flow, self.modulus)
+
+  def key(self):
+    return (self.charges.tobytes(), self.flow, self.modulus)
+
+
+def _signed(ix):
+  return -ix.charges if ix.flow else ix.charges
+
+
+def _fused_allowed(indices):
+  """flat row-major positions (stored order) whose fused charge is the identity."""
+  if not indices:
+    return np.zeros(1, dtype=np.int64)
+  mod = indices[0].modulus
+  fused = _signed(indices[0])
+  for ix in indices[1:]:
+    fused = np.add.outer(fused, _signed(ix)).ravel()
+  if mod:
+    fused = np.mod(fused, mod)
+  return np.nonzero(fused == 0)[0].astype(np.int64)
+
+
+def _sector_maps(indices, order, partition):
+  """Gather maps of the matrix view (legs order[:partition] | legs order[partition:]).
+
+  Returns (qnums, dims (nsect x 2), maps list) where maps[q] lists, row-major over the sector's
+  (rows x cols), the positions inside the flat data vector.  Sectors are ordered by ascending
+  row charge (the reference's `intersect`/`unique` ordering, blocksparse_utils.py:375-380)."""
+  key = ("sect", tuple(ix.key() for ix in indices), tuple(order), partition)
+  hit = _MAP_CACHE.get(key)
+  if hit is not None:
+    return hit
+  pos = _fused_allowed(indices)                       # sorted => data index = rank
+  dims = [ix.dim for ix in indices]
+  multi = np.unravel_index(pos, dims) if dims else ()
+  mod = indices[0].modulus if indices else None
+  rows = [order[i] for i in range(partition)]
+  cols = [order[i] for i in range(partition, len(order))]
+  R = np.zeros(pos.shape[0], dtype=np.int64)
+  rq = np.zeros(pos.shape[0], dtype=np.int64)
+  for leg in rows:
+    R = R * dims[leg] + multi[leg]
+    rq = rq + _signed(indices[leg])[multi[leg]]
+  C = np.zeros(pos.shape[0], dtype=np.int64)
+  for leg in cols:
+    C = C * dims[leg] + multi[leg]
+  if mod:
+    rq = np.mod(rq, mod)
+  perm = np.lexsort((C, R, rq))
+  rq_s = rq[perm]
+  qnums, starts, counts = np.unique(rq_s, return_index=True, return_counts=True)
+  maps, sdims = [], []
+  for s, c in zip(starts, counts):
+    idx = perm[s:s + c]
+    nrows = np.unique(R[idx]).shape[0]
+    maps.append(idx.astype(np.int64))
+    sdims.append((nrows, c // nrows))
+  out = (qnums, np.asarray(sdims, dtype=np.int64).reshape(-1, 2), maps)
+  _MAP_CACHE[key] = out
+  return out
+
+
+class BlockSparseTensor:
+  """Block-sparse tensor whose `data` vector lives in HBM (a 1-D B200Tensor)."""
+
+  def __init__(self, data, indices, order=None, backend=None):
+    from .backend import get_instance  # pylint: disable=import-outside-toplevel
+    self.backend = backend or get_instance()
+    self.indices = list(indices)
+    self.order = list(range(len(indices))) if order is None else list(order)
+    self.data = data
+
+  # ------------------------------------------------------------------ constructors
+  @classmethod
+  def _nnz(cls, indices):
+    return int(_fused_allowed(indices).shape[0])
+
+  @classmethod
+  def zeros(cls, indices, dtype=np.float64, backend=None):
+    from .backend import get_instance  # pylint: disable=import-outside-toplevel
+    be = backend or get_instance()
+    return cls(be.zeros((cls._nnz(indices),), dtype), indices, backend=be)
+
+  @classmethod
+  def randn(cls, indices, dtype=np.float64, seed=None, backend=None):
+    from .backend import get_instance  # pylint: disable=import-outside-toplevel
+    be = backend or get_instance()
+    return cls(be.randn((cls._nnz(indices),), dtype, seed=seed), indices, backend=be)
+
+  @classmethod
+  def random(cls, indices, boundaries=(0.0, 1.0), dtype=np.float64, seed=None, backend=None):
+    from .backend import get_instance  # pylint: disable=import-outside-toplevel
+    be = backend or get_instance()
+    return cls(be.random_uniform((cls._nnz(indices),), boundaries, dtype, seed=seed), indices, backend=be)
+
+  @classmethod
+  def from_data(cls, data, indices, order=None, backend=None):
+    """wrap a host data vector laid out like the reference's `BlockSparseTensor.data`."""
+    from .backend import get_instance  # pylint: disable=import-outside-toplevel
+    be = backend or get_instance()
+    data = np.ascontiguousarray(data).ravel()
+    if data.shape[0] != cls._nnz(indices):
+      raise ValueError("data has {} elements, the charges allow {}".format(data.shape[0], cls._nnz(indices)))
+    return cls(be.convert_to_tensor(data), indices, order, backend=be)
+
+  @classmethod
+  def fromdense(cls, indices, array, backend=None):
+    """blocksparsetensor.py:534-573: keep the symmetry-allowed elements of a dense array."""
+    array = np.asarray(array)
+    if tuple(array.shape) != tuple(ix.dim for ix in indices):
+      raise ValueError("Cannot initialize an BlockSparseTensor of shape {} from an array of shape {}".format(
+          tuple(ix.dim for ix in indices), array.shape))
+    return cls.from_data(array.ravel()[_fused_allowed(indices)], indices, backend=backend)
+
+  # ------------------------------------------------------------------ metadata
+  @property
+  def ndim(self):
+    return len(self.indices)
+
+  @property
+  def shape(self):
+    return tuple(self.indices[i].dim for i in self.order)
+
+  @property
+  def dtype(self):
+    return self.data.dtype
+
+  @property
+  def flows(self):
+    return [self.indices[i].flow for i in self.order]
+
+  def todense(self):
+    """blocksparsetensor.py:575-589 (host side: used by tests / user inspection)."""
+    dims = [ix.dim for ix in self.indices]
+    host = self.data.to_host()
+    out = np.zeros(int(np.prod(dims)) if dims else 1, dtype=host.dtype)
+    out[_fused_allowed(self.indices)] = host
+    return out.reshape(dims).transpose(self.order) if dims else out.reshape(())
+
+  def transpose(self, order=None):
+    """lazy: only the logical order changes (blocksparsetensor.py:738-760)."""
+    if order is None:
+      order = list(reversed(range(self.ndim)))
+    if sorted(order) != list(range(self.ndim)):
+      raise ValueError("order = {} is not a permutation".format(order))
+    return BlockSparseTensor(self.data, self.indices, [self.order[i] for i in order], self.backend)
+
+  def conj(self):
+    """blocksparsetensor.py:723-736: conjugate the data, flip every flow."""
+    return BlockSparseTensor(self.backend.conj(self.data), [ix.flip_flow() for ix in self.indices],
+                             self.order, self.backend)
+
+  def __mul__(self, number):
+    return BlockSparseTensor(self.data * number, self.indices, self.order, self.backend)
+
+  __rmul__ = __mul__
+
+  def __add__(self, other):
+    self._same_structure(other)
+    return BlockSparseTensor(self.data + other.data, self.indices, self.order, self.backend)
+
+  def __sub__(self, other):
+    self._same_structure(other)
+    return BlockSparseTensor(self.data - other.data, self.indices, self.order, self.backend)
+
+  def _same_structure(self, other):
+    if self.order != other.order or [i.key() for i in self.indices] != [i.key() for i in other.indices]:
+      raise ValueError("cannot combine tensors with non-matching charges / flows / orders")
+
+
+def tensordot(a, b, axes):
+  """block_sparse.tensordot (blocksparsetensor.py:925-1108) — all charge sectors in one launch.
+
+  Result legs: free legs of `a` (logical order) then free legs of `b`; same data layout as the
+  reference (fresh tensor, identity order)."""
+  be = a.backend
+  if isinstance(axes, (int, np.integer)):
+    n = int(axes)
+    axes_a = list(range(a.ndim - n, a.ndim))
+    axes_b = list(range(n))
+  else:
+    axes_a = [int(x) for x in (axes[0] if not isinstance(axes[0], (int, np.integer)) else [axes[0]])]
+    axes_b = [int(x) for x in (axes[1] if not isinstance(axes[1], (int, np.integer)) else [axes[1]])]
+  if len(axes_a) != len(axes_b):
+    raise ValueError("`axes1 = {}` and `axes2 = {}` have to be of same length.".format(axes_a, axes_b))
+  if len(axes_a) > a.ndim or len(axes_b) > b.ndim:
+    raise ValueError("too many axes for the given tensors")
+  if len(set(axes_a)) != len(axes_a) or len(set(axes_b)) != len(axes_b):
+    raise ValueError("Some values in axes appear more than once")
+  if a.data.code != b.data.code:
+    raise ValueError("tensor1 and tensor2 have different dtypes")
+  # contracted legs need equal charges and opposite flows (blocksparsetensor.py:985-1015)
+  for x, y in zip(axes_a, axes_b):
+    ia, ib = a.indices[a.order[x]], b.indices[b.order[y]]
+    if ia.dim != ib.dim:
+      raise ValueError("axes1 and axes2 have incompatible elementary shapes")
+    if ia.flow == ib.flow:
+      raise ValueError("axes1 and axes2 have incompatible elementary flows")
+    if not np.array_equal(ia.charges, ib.charges):
+      raise ValueError("axes1 and axes2 have incompatible elementary charges")
+  free_a = [i for i in range(a.ndim) if i not in axes_a]
+  free_b = [i for i in range(b.ndim) if i not in axes_b]
+  out_indices = [a.indices[a.order[i]] for i in free_a] + [b.indices[b.order[i]] for i in free_b]
+  # matrix views: A = (free_a | axes_a), B = (axes_b | free_b), C = (free_a | free_b)
+  order_a = [a.order[i] for i in free_a] + [a.order[i] for i in axes_a]
+  order_b = [b.order[i] for i in axes_b] + [b.order[i] for i in free_b]
+  qa, da, ma = _sector_maps(a.indices, order_a, len(free_a))
+  qb, db, mb = _sector_maps(b.indices, order_b, len(axes_b))
+  qc, dc, mc = _sector_maps(out_indices, list(range(len(out_indices))), len(free_a))
+  nnz_c = BlockSparseTensor._nnz(out_indices)  # pylint: disable=protected-access
+  c_data = be.zeros((nnz_c,), a.data.dtype)      # blocksparsetensor.py:1088: zero-initialised
+  mod = a.indices[0].modulus if a.indices else None
+  # B's row charge equals A's row charge within a sector (opposite flows on contracted legs);
+  sect = []
+  posb = {int(q): i for i, q in enumerate(qb)}
+  posc = {int(q): i for i, q in enumerate(qc)}
+  for i, q in enumerate(qa):
+    q = int(q)
+    if q in posb and q in posc:
+      j, k = posb[q], posc[q]
+      m_, k_ = int(da[i, 0]), int(da[i, 1])
+      kb_, n_ = int(db[j, 0]), int(db[j, 1])
+      if k_ != kb_ or int(dc[k, 0]) != m_ or int(dc[k, 1]) != n_:
+        raise RuntimeError("block-sparse sector bookkeeping mismatch (internal error)")
+      sect.append((i, j, k, m_, k_, n_))
+  if not sect or nnz_c == 0:
+    return BlockSparseTensor(c_data, out_indices, backend=be)
+  key = ("td", id(ma), id(mb), id(mc), tuple(s[:3] for s in sect))
+  dev = _MAP_CACHE.get(key)
+  if dev is None:
+    torch = be.torch
+    dims = np.asarray([[s[3], s[4], s[5]] for s in sect], dtype=np.int64)
+
+    def cat(maps, which):
+      arrs = [maps[s[which]] for s in sect]
+      off = np.zeros(len(arrs) + 1, dtype=np.int64)
+      off[1:] = np.cumsum([x.shape[0] for x in arrs])
+      return np.concatenate(arrs), off
+    am, ao = cat(ma, 0)
+    bm, bo = cat(mb, 1)
+    cm, co = cat(mc, 2)
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(be.device)
+    dev = dict(dims=up(dims), am=up(am), ao=up(ao), bm=up(bm), bo=up(bo), cm=up(cm), co=up(co),
+               max_m=int(dims[:, 0].max()), max_n=int(dims[:, 2].max()), nsect=len(sect),
+               keep=(ma, mb, mc), flops=float(2 * (dims[:, 0] * dims[:, 1] * dims[:, 2]).sum()))
+    _MAP_CACHE[key] = dev
+  rc = be.lib.tnb200_blocksparse_tensordot(
+      a.data.t.data_ptr(), b.data.t.data_ptr(), c_data.t.data_ptr(), a.data.code, dev["nsect"],
+      dev["dims"].data_ptr(), dev["am"].data_ptr(), dev["ao"].data_ptr(), dev["bm"].data_ptr(),
+      dev["bo"].data_ptr(), dev["cm"].data_ptr(), dev["co"].data_ptr(), dev["max_m"], dev["max_n"], 0,
+      be._stream())  # pylint: disable=protected-access
+  L.check(rc)
+  out = BlockSparseTensor(c_data, out_indices, backend=be)
+  out.last_flops = dev["flops"]
+  return out

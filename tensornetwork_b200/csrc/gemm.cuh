@@ -1,16 +1,29 @@
-// gemm.cuh — the canonical (batched, strided) GEMM problem the tensordot planner lowers to.
+// gemm.cuh — the canonical (batched, strided, multi-mode) GEMM problem the tensordot planner lowers to.
 #pragma once
 #include "common.cuh"
 
 namespace tnb {
 
-// C[b, m, n] = sum_k opA(A[b, m, k]) * opB(B[b, k, n]); all strides in elements.
+// One operand as a (batch, free modes, contracted modes) view.  Modes are listed outer -> inner
+// (row-major linearisation of the group), strides in elements.  A group with one mode is a
+// plain matrix dimension; up to two modes per group can be addressed directly by the TMA path.
+struct OperandView {
+  const void* ptr = nullptr;
+  int nF = 0, nK = 0;
+  int64_t fe[4] = {1, 1, 1, 1}, fs[4] = {0, 0, 0, 0};
+  int64_t ke[4] = {1, 1, 1, 1}, ks[4] = {0, 0, 0, 0};
+  int64_t sb = 0;  // batch stride
+  bool simple() const { return nF <= 1 && nK <= 1; }
+  int64_t f_stride() const { return nF ? fs[nF - 1] : 0; }   // innermost free stride
+  int64_t k_stride() const { return nK ? ks[nK - 1] : 0; }   // innermost contracted stride
+};
+
+// C[b, m, n] = sum_k A[b, m, k] * B[b, k, n]; C is a 2-stride matrix per batch entry.
 struct GemmProblem {
   int dtype = 0;
   int64_t M = 0, N = 0, K = 0, batch = 1;
-  const void* A = nullptr; int64_t a_sm = 0, a_sk = 0, a_sb = 0;
-  const void* B = nullptr; int64_t b_sk = 0, b_sn = 0, b_sb = 0;
-  void* C = nullptr;       int64_t c_sm = 0, c_sn = 0, c_sb = 0;
+  OperandView A, B;
+  void* C = nullptr; int64_t c_sm = 0, c_sn = 0, c_sb = 0;
   bool conjA = false, conjB = false;
   int math = 0;  // TNB200_MATH_* >> 4
 };
@@ -19,7 +32,7 @@ struct GemmProblem {
 // meet the kernel's layout/alignment constraints; the planner then repacks or falls back.
 int gemm_tcgen05(const GemmProblem& p, cudaStream_t st);   // bf16 / f16 / f32(tf32)
 int gemm_dmma_f64(const GemmProblem& p, cudaStream_t st);  // f64 via mma.sync DMMA
-bool tcgen05_operand_ok(int dtype, const void* ptr, int64_t ext_mn, int64_t ext_k,
-                        int64_t s_mn, int64_t s_k, int64_t s_b, int64_t batch);
+// can the TMA/UMMA path address this operand view in place?  (tile-size independent check)
+bool tcgen05_view_ok(int dtype, const OperandView& v, int64_t ext_f, int64_t ext_k, int64_t batch);
 
 }  // namespace tnb

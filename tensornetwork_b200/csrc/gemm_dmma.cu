@@ -164,11 +164,12 @@ static int launch_dmma(const DmmaParams& p, int64_t tiles, cudaStream_t st) {
 int gemm_dmma_f64(const GemmProblem& g, cudaStream_t st) {
   if (g.dtype != TNB200_F64 || g.conjA || g.conjB) return TNB200_ERR_UNSUPPORTED;
   if (g.c_sn != 1 && g.N > 1) return TNB200_ERR_UNSUPPORTED;
+  if (!g.A.simple() || !g.B.simple()) return TNB200_ERR_UNSUPPORTED;
   DmmaParams p;
-  p.A = (const double*)g.A; p.B = (const double*)g.B; p.C = (double*)g.C;
+  p.A = (const double*)g.A.ptr; p.B = (const double*)g.B.ptr; p.C = (double*)g.C;
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
-  p.a_sm = g.a_sm; p.a_sk = g.a_sk; p.a_sb = g.a_sb;
-  p.b_sk = g.b_sk; p.b_sn = g.b_sn; p.b_sb = g.b_sb;
+  p.a_sm = g.A.f_stride(); p.a_sk = g.A.k_stride(); p.a_sb = g.A.sb;
+  p.b_sk = g.B.k_stride(); p.b_sn = g.B.f_stride(); p.b_sb = g.B.sb;
   p.c_sm = g.c_sm; p.c_sb = g.c_sb;
   p.vec_ok = (((uintptr_t)g.C) % 16 == 0) && (g.c_sm % 2 == 0) && (g.c_sb % 2 == 0);
   p.tiles_m = (g.M + DBM - 1) / DBM;
@@ -179,8 +180,8 @@ int gemm_dmma_f64(const GemmProblem& g, cudaStream_t st) {
   const int64_t tiles = p.tiles_m * p.tiles_n * g.batch;
   if (tiles >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
   // an operand is loaded "K-major" when its contracted stride is the smaller one
-  const bool a_k = llabs(g.a_sk) <= llabs(g.a_sm) || g.M == 1;
-  const bool b_k = llabs(g.b_sk) <= llabs(g.b_sn) || g.N == 1;
+  const bool a_k = llabs(p.a_sk) <= llabs(p.a_sm) || g.M == 1;
+  const bool b_k = llabs(p.b_sk) <= llabs(p.b_sn) || g.N == 1;
   set_kernel_name("dmma_f64");
 #define TNB_DMMA(BNV)                                                           \
   if (a_k && b_k) return launch_dmma<BNV, true, true>(p, tiles, st);            \

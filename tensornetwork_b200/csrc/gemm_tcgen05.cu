@@ -47,10 +47,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
   __trap();
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -100,6 +100,10 @@ struct TcParams {
   int BN, num_kb, stages, out_kind;   // out_kind: 0 bf16, 1 f16, 2 f32
   int64_t tiles_m, tiles_n, num_tiles;
   int a_mn, b_mn;                     // operand is MN-major
+  // multi-mode operands: extent of the INNER free / contracted mode (0 = the group is one mode).
+  // TMA dims are always (K-major)  [k_in, f_in, f_out, k_out, batch]
+  //                     (MN-major) [f_in, k_in, k_out, f_out, batch]
+  uint32_t a_fe, a_ke, b_fe, b_ke;
   uint32_t idesc;
   void* C; int64_t c_sm, c_sb;        // c_sn == 1
   int vec_ok;
@@ -170,18 +174,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
         const uint32_t sb = sa + A_BYTES;
         const int k0 = kb * BK;
+        // split linear indices into (outer, inner) mode coordinates
+        const int ak_in = p.a_ke ? (int)(k0 % p.a_ke) : k0, ak_out = p.a_ke ? (int)(k0 / p.a_ke) : 0;
+        const int bk_in = p.b_ke ? (int)(k0 % p.b_ke) : k0, bk_out = p.b_ke ? (int)(k0 / p.b_ke) : 0;
         if (!p.a_mn) {
-          tma_load_3d(sa, &tmA, full_bar(s), k0, m0, bi);
+          const int f_in = p.a_fe ? (int)(m0 % p.a_fe) : m0, f_out = p.a_fe ? (int)(m0 / p.a_fe) : 0;
+          tma_load_5d(sa, &tmA, full_bar(s), ak_in, f_in, f_out, ak_out, bi);
         } else {
 #pragma unroll
-          for (int c = 0; c < kBM / CHUNK; ++c)
-            tma_load_3d(sa + c * (BK * kRowBytes), &tmA, full_bar(s), m0 + c * CHUNK, k0, bi);
+          for (int c = 0; c < kBM / CHUNK; ++c) {
+            const int f = m0 + c * CHUNK;
+            const int f_in = p.a_fe ? (int)(f % p.a_fe) : f, f_out = p.a_fe ? (int)(f / p.a_fe) : 0;
+            tma_load_5d(sa + c * (BK * kRowBytes), &tmA, full_bar(s), f_in, ak_in, ak_out, f_out, bi);
+          }
         }
         if (!p.b_mn) {
-          tma_load_3d(sb, &tmB, full_bar(s), k0, n0, bi);
+          const int f_in = p.b_fe ? (int)(n0 % p.b_fe) : n0, f_out = p.b_fe ? (int)(n0 / p.b_fe) : 0;
+          tma_load_5d(sb, &tmB, full_bar(s), bk_in, f_in, f_out, bk_out, bi);
         } else {
-          for (int c = 0; c < BN / CHUNK; ++c)
-            tma_load_3d(sb + c * (BK * kRowBytes), &tmB, full_bar(s), n0 + c * CHUNK, k0, bi);
+          for (int c = 0; c < BN / CHUNK; ++c) {
+            const int f = n0 + c * CHUNK;
+            const int f_in = p.b_fe ? (int)(f % p.b_fe) : f, f_out = p.b_fe ? (int)(f / p.b_fe) : 0;
+            tma_load_5d(sb + c * (BK * kRowBytes), &tmB, full_bar(s), f_in, bk_in, bk_out, f_out, bi);
+          }
         }
         if (++s == S) { s = 0; ph ^= 1; }
       }
@@ -310,61 +325,106 @@ static EncodeTiledFn get_encode() {
 
 static int es_of(int dt) { return dt == TNB200_F32 ? 4 : 2; }
 
-bool tcgen05_operand_ok(int dtype, const void* ptr, int64_t ext_mn, int64_t ext_k, int64_t s_mn, int64_t s_k,
-                        int64_t s_b, int64_t batch) {
-  if (dtype != TNB200_F32 && dtype != TNB200_F16 && dtype != TNB200_BF16) return false;
-  const int es = es_of(dtype);
-  if (((uintptr_t)ptr) & 15) return false;
-  if (ext_mn >= (1LL << 31) || ext_k >= (1LL << 31) || batch >= (1LL << 31)) return false;
-  auto ok16 = [&](int64_t s) { return s > 0 && (s * es) % 16 == 0 && s * es < (1LL << 40); };
-  if (batch > 1 && !ok16(s_b)) return false;
-  const bool k_unit = (s_k == 1 || ext_k == 1), mn_unit = (s_mn == 1 || ext_mn == 1);
-  if (k_unit && (ext_mn == 1 || ok16(s_mn))) return true;   // K-major
-  if (mn_unit && (ext_k == 1 || ok16(s_k))) {
-    if (dtype == TNB200_F32) {
-      static int tf32_mn = -1;
-      if (tf32_mn < 0) { const char* e = getenv("TNB200_TF32_MN"); tf32_mn = (e && e[0] == '0') ? 0 : 1; }
-      return tf32_mn == 1;
-    }
-    return true;  // MN-major
-  }
-  return false;
+static bool tf32_mn_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("TNB200_TF32_MN"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
-static int encode_operand(CUtensorMap* map, int dtype, const void* ptr, int64_t ext_mn, int64_t ext_k, int64_t s_mn,
-                          int64_t s_k, int64_t s_b, int64_t batch, int box_mn, bool& mn_major) {
+// Which UMMA majorness can serve this view?  0: K-major, 1: MN-major, -1: neither (needs a repack).
+// Conditions (es = element bytes, R = 128/es elements per swizzle row):
+//   * unit stride on the innermost contracted mode (K-major) or innermost free mode (MN-major);
+//   * every other stride and the base pointer 16-byte aligned; rank <= 5 (<= 2 modes per group);
+//   * two contracted modes: inner extent % R == 0 (a k-block never straddles the mode boundary);
+//   * two free modes: MN-major: inner extent % R == 0;  K-major: inner extent % 256 == 0, or a
+//     power of two <= 64 (so every tile size 64/128/256 either divides it or is a multiple of it).
+static int view_major(int dtype, const OperandView& v, int64_t ext_f, int64_t ext_k, int64_t batch) {
+  if (dtype != TNB200_F32 && dtype != TNB200_F16 && dtype != TNB200_BF16) return -1;
+  const int es = es_of(dtype);
+  const int64_t R = kRowBytes / es;
+  if (((uintptr_t)v.ptr) & 15) return -1;
+  if (v.nF > 2 || v.nK > 2) return -1;
+  if (ext_f >= (1LL << 31) || ext_k >= (1LL << 31) || batch >= (1LL << 31)) return -1;
+  auto ok16 = [&](int64_t s) { return s > 0 && (s * es) % 16 == 0 && s * es < (1LL << 40); };
+  if (batch > 1 && !ok16(v.sb)) return -1;
+  if (v.nK == 2 && v.ke[1] % R != 0) return -1;
+  const bool k_unit = ext_k == 1 || v.nK == 0 || v.ks[v.nK - 1] == 1;
+  const bool f_unit = ext_f == 1 || v.nF == 0 || v.fs[v.nF - 1] == 1;
+  if (k_unit) {  // K-major candidate: all free strides + outer K stride must be 16B multiples
+    bool ok = true;
+    for (int i = 0; i < v.nF; ++i) ok = ok && (v.fe[i] == 1 || ok16(v.fs[i]));
+    if (v.nK == 2) ok = ok && ok16(v.ks[0]);
+    if (v.nF == 2) { int64_t e = v.fe[1]; ok = ok && (e % 256 == 0 || (e <= 64 && (e & (e - 1)) == 0)); }
+    if (ok) return 0;
+  }
+  if (f_unit) {
+    bool ok = true;
+    for (int i = 0; i < v.nK; ++i) ok = ok && (v.ke[i] == 1 || ok16(v.ks[i]));
+    if (v.nF == 2) ok = ok && ok16(v.fs[0]) && (v.fe[1] % R == 0);
+    if (dtype == TNB200_F32 && !tf32_mn_enabled()) ok = false;
+    if (ok) return 1;
+  }
+  return -1;
+}
+
+bool tcgen05_view_ok(int dtype, const OperandView& v, int64_t ext_f, int64_t ext_k, int64_t batch) {
+  return view_major(dtype, v, ext_f, ext_k, batch) >= 0;
+}
+
+// Build the rank-5 tensor map of one operand for tiles of `tile` free rows.
+static int encode_operand(CUtensorMap* map, int dtype, const OperandView& v, int64_t ext_f, int64_t ext_k, int64_t batch,
+                          int tile, bool& mn_major, uint32_t& fe_in, uint32_t& ke_in) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return TNB200_ERR_UNSUPPORTED;
+  const int major = view_major(dtype, v, ext_f, ext_k, batch);
+  if (major < 0) return TNB200_ERR_UNSUPPORTED;
+  mn_major = major == 1;
   const int es = es_of(dtype);
-  const int bk = kRowBytes / es, chunk = kRowBytes / es;
-  const bool k_unit = (s_k == 1 || ext_k == 1);
-  const bool k_major = k_unit && (ext_mn == 1 || (s_mn * es) % 16 == 0);
-  mn_major = !k_major;
+  const int R = kRowBytes / es;
   CUtensorMapDataType cdt = dtype == TNB200_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                             : (dtype == TNB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-  cuuint64_t dims[3], strides[2];
-  cuuint32_t box[3], estr[3] = {1, 1, 1};
-  // a stride that is never used for addressing (extent 1) still has to be a valid multiple of 16 B
-  auto fix = [&](int64_t s, int64_t fallback_elems) -> cuuint64_t {
-    int64_t b = s * es;
-    if (b <= 0 || b % 16) b = ((fallback_elems * es + 15) / 16) * 16;
-    return (cuuint64_t)b;
-  };
-  CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  if (k_major) {
-    dims[0] = (cuuint64_t)ext_k; dims[1] = (cuuint64_t)ext_mn; dims[2] = (cuuint64_t)batch;
-    strides[0] = ext_mn == 1 ? fix(0, ext_k) : (cuuint64_t)(s_mn * es);
-    strides[1] = batch == 1 ? fix(0, ext_k * ext_mn) : (cuuint64_t)(s_b * es);
-    box[0] = bk; box[1] = box_mn; box[2] = 1;
+  // (extent, stride) of inner / outer mode of each group; missing modes are extent 1
+  int64_t f_in_e = v.nF ? v.fe[v.nF - 1] : 1, f_in_s = v.nF ? v.fs[v.nF - 1] : 0;
+  int64_t f_out_e = v.nF == 2 ? v.fe[0] : 1, f_out_s = v.nF == 2 ? v.fs[0] : 0;
+  int64_t k_in_e = v.nK ? v.ke[v.nK - 1] : 1, k_in_s = v.nK ? v.ks[v.nK - 1] : 0;
+  int64_t k_out_e = v.nK == 2 ? v.ke[0] : 1, k_out_s = v.nK == 2 ? v.ks[0] : 0;
+  fe_in = v.nF == 2 ? (uint32_t)f_in_e : 0u;
+  ke_in = v.nK == 2 ? (uint32_t)k_in_e : 0u;
+  int64_t de[5], ds[5];   // extents, element strides (ds[0] is the unit-stride dim)
+  cuuint32_t box[5] = {1, 1, 1, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+  if (!mn_major) {
+    de[0] = k_in_e; ds[0] = 1;
+    de[1] = f_in_e; ds[1] = f_in_s; de[2] = f_out_e; ds[2] = f_out_s;
+    de[3] = k_out_e; ds[3] = k_out_s; de[4] = batch; ds[4] = v.sb;
+    box[0] = R;
+    if (v.nF == 2 && f_in_e < tile) {
+      if (tile % f_in_e) return TNB200_ERR_UNSUPPORTED;
+      box[1] = (cuuint32_t)f_in_e; box[2] = (cuuint32_t)(tile / f_in_e);
+    } else {
+      if (v.nF == 2 && f_in_e % tile) return TNB200_ERR_UNSUPPORTED;
+      box[1] = tile;
+    }
   } else {
-    dims[0] = (cuuint64_t)ext_mn; dims[1] = (cuuint64_t)ext_k; dims[2] = (cuuint64_t)batch;
-    strides[0] = ext_k == 1 ? fix(0, ext_mn) : (cuuint64_t)(s_k * es);
-    strides[1] = batch == 1 ? fix(0, ext_k * ext_mn) : (cuuint64_t)(s_b * es);
-    box[0] = chunk; box[1] = bk; box[2] = 1;
-    if (dtype == TNB200_F32) sw = CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    de[0] = f_in_e; ds[0] = 1;
+    de[1] = k_in_e; ds[1] = k_in_s; de[2] = k_out_e; ds[2] = k_out_s;
+    de[3] = f_out_e; ds[3] = f_out_s; de[4] = batch; ds[4] = v.sb;
+    box[0] = R; box[1] = R;   // R elements of the free mode (128 B) x BK = R contracted rows
   }
-  if (strides[1] % 16) strides[1] = ((strides[1] + 15) / 16) * 16;
-  CUresult r = enc(map, cdt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+  cuuint64_t dims[5], strides[4];
+  int64_t natural = 16;   // bytes: a packed stride for extent-1 (never addressed) dims
+  for (int d = 0; d < 5; ++d) {
+    dims[d] = (cuuint64_t)(de[d] < 1 ? 1 : de[d]);
+    int64_t bytes = es;
+    if (d > 0) {
+      bytes = ds[d] * es;
+      if (de[d] <= 1) bytes = (natural + 15) / 16 * 16;
+      else if (bytes <= 0 || bytes % 16) return TNB200_ERR_UNSUPPORTED;
+      strides[d - 1] = (cuuint64_t)bytes;
+    }
+    if ((int64_t)dims[d] * bytes > natural) natural = (int64_t)dims[d] * bytes;
+  }
+  CUtensorMapSwizzle sw = (mn_major && dtype == TNB200_F32) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(map, cdt, 5, const_cast<void*>(v.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return TNB200_ERR_UNSUPPORTED;
   return 0;
@@ -380,8 +440,7 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
   if (g.conjA || g.conjB) return TNB200_ERR_UNSUPPORTED;
   if (g.c_sn != 1 && g.N > 1) return TNB200_ERR_UNSUPPORTED;
   if (g.M >= (1LL << 31) || g.N >= (1LL << 31) || g.K >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
-  if (!tcgen05_operand_ok(g.dtype, g.A, g.M, g.K, g.a_sm, g.a_sk, g.a_sb, g.batch) ||
-      !tcgen05_operand_ok(g.dtype, g.B, g.N, g.K, g.b_sn, g.b_sk, g.b_sb, g.batch))
+  if (!tcgen05_view_ok(g.dtype, g.A, g.M, g.K, g.batch) || !tcgen05_view_ok(g.dtype, g.B, g.N, g.K, g.batch))
     return TNB200_ERR_UNSUPPORTED;
   const int es = es_of(g.dtype);
   const int sms = num_sms();
@@ -413,9 +472,9 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
   p.vec_ok = (((uintptr_t)g.C) % 16 == 0) && ((g.c_sm * es) % 16 == 0) && ((g.c_sb * es) % 16 == 0);
   CUtensorMap tmA, tmB;
   bool a_mn = false, b_mn = false;
-  int rc = encode_operand(&tmA, g.dtype, g.A, g.M, g.K, g.a_sm, g.a_sk, g.a_sb, g.batch, kBM, a_mn);
+  int rc = encode_operand(&tmA, g.dtype, g.A, g.M, g.K, g.batch, kBM, a_mn, p.a_fe, p.a_ke);
   if (rc) return rc;
-  rc = encode_operand(&tmB, g.dtype, g.B, g.N, g.K, g.b_sn, g.b_sk, g.b_sb, g.batch, BN, b_mn);
+  rc = encode_operand(&tmB, g.dtype, g.B, g.N, g.K, g.batch, BN, b_mn, p.b_fe, p.b_ke);
   if (rc) return rc;
   p.a_mn = a_mn; p.b_mn = b_mn;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B format, majors, N>>3, M>>4

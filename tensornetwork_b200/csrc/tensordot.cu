@@ -297,49 +297,83 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
       GemmProblem g;
       g.dtype = dt; g.M = M; g.N = N; g.K = K; g.batch = Bt; g.conjA = conjA; g.conjB = conjB; g.math = math;
       g.C = c->data; g.c_sm = cm_s; g.c_sn = cn_s; g.c_sb = gB.n ? gB.s2[0] : 0;
-      void *packA = nullptr, *packB = nullptr;
-      // choose a K ordering under which as many operands as possible are plain 2-stride matrices
-      int best = -1, best_score = -1; bool bestA = false, bestB = false;
-      int64_t am_e = 0, am_s = 0, ak_s = 0, bn_e = 0, bn_s = 0, bk_s = 0, tmp_e;
-      for (int cand = 0; cand < 2; ++cand) {
+      // Build both operand views under a common ordering of the contracted modes; try the order
+      // that sorts them by A's strides and the one that sorts by B's, keep the one under which
+      // more operands are addressable in place (TMA for 16/32-bit, 2-stride cp.async for f64).
+      auto make_views = [&](int cand, OperandView& va, OperandView& vb) -> bool {
         ModeList ko = order_k(mK, cand);
-        int64_t e1, s1, e2, s2, e3, s3, e4, s4;
-        bool okA = single_mode(gM, 0, e1, s1) && single_mode(ko, 0, e2, s2);
-        bool okB = single_mode(gN, 0, e3, s3) && single_mode(ko, 1, e4, s4);
-        if (dt != TNB200_F64) {
-          okA = okA && tcgen05_operand_ok(dt, a->data, M, K, s1, s2, gB.n ? gB.s0[0] : 0, Bt);
-          okB = okB && tcgen05_operand_ok(dt, b->data, N, K, s3, s4, gB.n ? gB.s1[0] : 0, Bt);
-        }
+        merge_modes(ko, 2);                 // joint merge keeps A's and B's k orders identical
+        if (ko.n > 4 || gM.n > 4 || gN.n > 4) return false;
+        va = OperandView(); vb = OperandView();
+        va.ptr = a->data; vb.ptr = b->data;
+        va.nF = gM.n; for (int i = 0; i < gM.n; ++i) { va.fe[i] = gM.ext[i]; va.fs[i] = gM.s0[i]; }
+        vb.nF = gN.n; for (int i = 0; i < gN.n; ++i) { vb.fe[i] = gN.ext[i]; vb.fs[i] = gN.s0[i]; }
+        va.nK = vb.nK = ko.n;
+        for (int i = 0; i < ko.n; ++i) { va.ke[i] = vb.ke[i] = ko.ext[i]; va.ks[i] = ko.s0[i]; vb.ks[i] = ko.s1[i]; }
+        va.sb = gB.n ? gB.s0[0] : 0; vb.sb = gB.n ? gB.s1[0] : 0;
+        return true;
+      };
+      auto view_ok = [&](const OperandView& v, int64_t ef) -> bool {
+        if (dt == TNB200_F64) return v.simple();
+        return tcgen05_view_ok(dt, v, ef, K, Bt);
+      };
+      int best = -1, best_score = -1; bool bestA = false, bestB = false;
+      OperandView va, vb;
+      for (int cand = 0; cand < 2; ++cand) {
+        OperandView xa, xb;
+        if (!make_views(cand, xa, xb)) continue;
+        bool okA = view_ok(xa, M), okB = view_ok(xb, N);
         int score = (okA ? 1 : 0) + (okB ? 1 : 0);
-        if (score > best_score) {
-          best_score = score; best = cand; bestA = okA; bestB = okB;
-          if (okA) { am_e = e1; am_s = s1; ak_s = s2; }
-          if (okB) { bn_e = e3; bn_s = s3; bk_s = s4; }
+        if (score > best_score) { best_score = score; best = cand; bestA = okA; bestB = okB; va = xa; vb = xb; }
+      }
+      if (best >= 0) {
+        ModeList ko = order_k(mK, best);
+        merge_modes(ko, 2);
+        void *packA = nullptr, *packB = nullptr;
+        int rc = 0;
+        if (!bestA) {   // repack A as a contiguous K-major [batch, M, K] matrix (k in the common order)
+          rc = pack_operand(dt, a->data, gB, 0, gM, ko, 0, &packA, st);
+          va = OperandView(); va.ptr = packA; va.nF = 1; va.fe[0] = M; va.fs[0] = K; va.nK = 1; va.ke[0] = K; va.ks[0] = 1; va.sb = M * K;
         }
-      }
-      (void)am_e; (void)bn_e; (void)tmp_e;
-      ModeList ko = order_k(mK, best);
-      int rc = 0;
-      if (bestA) { g.A = a->data; g.a_sm = am_s; g.a_sk = ak_s; g.a_sb = gB.n ? gB.s0[0] : 0; }
-      else {
-        rc = pack_operand(dt, a->data, gB, 0, gM, ko, 0, &packA, st);
-        g.A = packA; g.a_sm = K; g.a_sk = 1; g.a_sb = M * K;
-      }
-      if (rc == 0) {
-        if (bestB) { g.B = b->data; g.b_sn = bn_s; g.b_sk = bk_s; g.b_sb = gB.n ? gB.s1[0] : 0; }
-        else {
+        if (rc == 0 && !bestB) {
           ModeList nB;  // free modes of B with B strides in slot 0
           for (int i = 0; i < gN.n; ++i) nB.push(gN.ext[i], gN.s0[i]);
           rc = pack_operand(dt, b->data, gB, 1, nB, ko, 1, &packB, st);
-          g.B = packB; g.b_sn = K; g.b_sk = 1; g.b_sb = N * K;
+          vb = OperandView(); vb.ptr = packB; vb.nF = 1; vb.fe[0] = N; vb.fs[0] = K; vb.nK = 1; vb.ke[0] = K; vb.ks[0] = 1; vb.sb = N * K;
         }
+        if (rc == 0) {
+          // a packed operand still contracts over ALL of K with one stride: collapse the other
+          // operand's view only if it is also single-mode; otherwise both keep `ko`'s mode split
+          if ((!bestA || !bestB) && (va.nK != vb.nK)) {
+            // the in-place operand has several k modes but the packed one has a single merged mode:
+            // give the packed operand the same split (contiguous, so strides are products)
+            OperandView& pk = !bestA ? va : vb;
+            const OperandView& ip = !bestA ? vb : va;
+            pk.nK = ip.nK;
+            int64_t st_ = 1;
+            for (int i = ip.nK - 1; i >= 0; --i) { pk.ke[i] = ip.ke[i]; pk.ks[i] = st_; st_ *= ip.ke[i]; }
+          }
+          g.A = va; g.B = vb;
+          rc = (dt == TNB200_F64) ? gemm_dmma_f64(g, st) : gemm_tcgen05(g, st);
+          if (rc == TNB200_ERR_UNSUPPORTED && (bestA || bestB) && !(packA && packB)) {
+            // in-place addressing was rejected at encode time (tile-size dependent): repack everything
+            if (!packA) {
+              rc = pack_operand(dt, a->data, gB, 0, gM, ko, 0, &packA, st);
+              va = OperandView(); va.ptr = packA; va.nF = 1; va.fe[0] = M; va.fs[0] = K; va.nK = 1; va.ke[0] = K; va.ks[0] = 1; va.sb = M * K;
+            } else { va.nK = 1; va.ke[0] = K; va.ks[0] = 1; }
+            if ((rc == 0 || rc == TNB200_ERR_UNSUPPORTED) && !packB) {
+              ModeList nB;
+              for (int i = 0; i < gN.n; ++i) nB.push(gN.ext[i], gN.s0[i]);
+              rc = pack_operand(dt, b->data, gB, 1, nB, ko, 1, &packB, st);
+              vb = OperandView(); vb.ptr = packB; vb.nF = 1; vb.fe[0] = N; vb.fs[0] = K; vb.nK = 1; vb.ke[0] = K; vb.ks[0] = 1; vb.sb = N * K;
+            } else if (packB) { vb.nK = 1; vb.ke[0] = K; vb.ks[0] = 1; }
+            if (rc == 0) { g.A = va; g.B = vb; rc = (dt == TNB200_F64) ? gemm_dmma_f64(g, st) : gemm_tcgen05(g, st); }
+          }
+        }
+        if (packA) ws_free(packA, st);
+        if (packB) ws_free(packB, st);
+        if (rc != TNB200_ERR_UNSUPPORTED) return rc;
       }
-      if (rc == 0) {
-        rc = (dt == TNB200_F64) ? gemm_dmma_f64(g, st) : gemm_tcgen05(g, st);
-      }
-      if (packA) ws_free(packA, st);
-      if (packB) ws_free(packB, st);
-      if (rc != TNB200_ERR_UNSUPPORTED) return rc;
     }
   }
   ModeList gK = mK;

@@ -84,3 +84,44 @@ def test_linearity_at_flagship_size():
   lhs = be.tensordot(be.addition(A1, A2), B, ([2], [0]))
   rhs = be.addition(be.tensordot(A1, B, ([2], [0])), be.tensordot(A2, B, ([2], [0])))
   assert rel_err(lhs.to_host(), rhs.to_host()) < 2e-3
+
+
+def _launches(be):
+  return be.lib.tnb200_launch_count()
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float32"])
+def test_multimode_operands_are_fused_not_repacked(dtype):
+  """Operands whose free / contracted group is two non-mergeable modes are addressed in place by
+  rank-5 TMA maps: exactly ONE kernel launch (no strided-copy repack), results within tolerance."""
+  be = get_backend()
+  rng = np.random.default_rng(26)
+  # (b) of the cfg-2 zipper: A(512,2,512) x T(2,512,512) over A axes (0,1) <-> T axes (2,0)
+  A, a = _mk(be, rng, (512, 2, 512), dtype)
+  Tt, t = _mk(be, rng, (2, 512, 512), dtype)
+  l0 = _launches(be)
+  out = be.tensordot(A, Tt, ([0, 1], [2, 0]))
+  assert _launches(be) - l0 == 1, "repacked: %d launches" % (_launches(be) - l0)
+  assert be.lib.tnb200_last_kernel().decode().startswith("tcgen05")
+  assert rel_err(out.to_host(), np.tensordot(a, t, ([0, 1], [2, 0]))) < TOLS[dtype]
+  # free group = two modes around the contracted physical leg (MN-major, inner extent % 64 == 0)
+  X, x = _mk(be, rng, (256, 4, 128), dtype)
+  Y, y = _mk(be, rng, (4, 192), dtype)
+  l0 = _launches(be)
+  out = be.tensordot(X, Y, ([1], [0]))
+  assert _launches(be) - l0 == 1
+  assert rel_err(out.to_host(), np.tensordot(x, y, ([1], [0]))) < TOLS[dtype]
+  # K-major operand with two free modes (a slice breaks mergeability), power-of-two inner extent
+  Z, z = _mk(be, rng, (8, 64, 256), dtype)
+  Zs = Z[:, :32, :]
+  W, w = _mk(be, rng, (256, 64), dtype)
+  l0 = _launches(be)
+  out = be.tensordot(Zs, W, ([2], [0]))
+  assert _launches(be) - l0 == 1
+  assert rel_err(out.to_host(), np.tensordot(z[:, :32, :], w, ([2], [0]))) < TOLS[dtype]
+  # batched + multi-mode
+  Ab, ab = _mk(be, rng, (3, 256, 2, 128), dtype)
+  Bb, bb = _mk(be, rng, (3, 2, 64, 256), dtype)
+  out = be._contract(Ab, Bb, [1, 2], [3, 1], [0], [0])
+  ref = np.einsum("bimk,bmji->bkj", ab, bb)
+  assert rel_err(out.to_host(), ref) < TOLS[dtype]
