@@ -257,6 +257,47 @@ def gen_lanczos(tn):
   _save("lanczos", meta, arrays)
 
 
+def gen_blocksparse(tn):
+  """block_sparse.tensordot (cfg 4 family): inputs, result data vector AND the reference's own
+  int64 block maps (`_find_transposed_diagonal_sparse_blocks`), so our map builder can be checked
+  bit-exactly ('int maps bit-exact')."""
+  from tensornetwork.block_sparse import BlockSparseTensor, Index, U1Charge, tensordot
+  from tensornetwork.block_sparse.blocksparse_utils import _find_transposed_diagonal_sparse_blocks
+  meta, arrays = [], {}
+  cases = [
+      # (seed, leg dim, charge range, flows, axes, transpose of A before the product)
+      (5, 8, 2, [False, False, True, True], ([2, 3], [2, 3]), None),
+      (6, 10, 3, [False, True, False, True], ([1, 3], [1, 3]), None),
+      (7, 6, 2, [True, False, False, True], ([0, 2], [0, 2]), (2, 0, 3, 1)),
+      (8, 12, 2, [False, False, True], ([2], [2]), None),
+      (5, 32, 8, [False, False, True, True], ([2, 3], [2, 3]), None),   # cfg 4 itself
+  ]
+  for ci, (seed, dim, q, flows, axes, perm) in enumerate(cases):
+    np.random.seed(seed)
+    legs = [Index(U1Charge.random(dim, -q, q), f) for f in flows]
+    A = BlockSparseTensor.random(legs, dtype=np.float64)
+    At = A if perm is None else A.transpose(perm)
+    Bc = At.conj()
+    C = tensordot(At, Bc, axes)
+    for li, leg in enumerate(legs):
+      arrays["c%d_q%d" % (ci, li)] = np.asarray(leg.flat_charges[0].charges).ravel().astype(np.int64)
+    arrays["c%d_A" % ci] = np.asarray(A.data)
+    arrays["c%d_C" % ci] = np.asarray(C.contiguous().data)
+    arrays["c%d_Cdense" % ci] = np.asarray(C.todense()) if dim <= 12 else np.zeros(0)
+    # the reference's gather maps of the first operand for this contraction
+    free1 = sorted(set(range(At.ndim)) - set(axes[0]))
+    new_order1 = [At._order[n] for n in free1] + [At._order[n] for n in axes[0]]
+    flat_order_1 = [x for sub in new_order1 for x in sub]
+    nleft = sum(len(At._order[n]) for n in free1)
+    blocks, qn, shapes = _find_transposed_diagonal_sparse_blocks(At._charges, At._flows, nleft, flat_order_1)
+    arrays["c%d_mapcat" % ci] = np.concatenate([np.asarray(b).ravel() for b in blocks]).astype(np.int64)
+    arrays["c%d_mapoff" % ci] = np.insert(np.cumsum([np.asarray(b).size for b in blocks]), 0, 0).astype(np.int64)
+    arrays["c%d_shapes" % ci] = np.asarray(shapes).astype(np.int64)
+    arrays["c%d_qnums" % ci] = np.asarray(qn.unique_charges).ravel().astype(np.int64)
+    meta.append(dict(flows=flows, axes=[list(axes[0]), list(axes[1])], perm=perm, nlegs=len(legs), dim=dim))
+  _save("blocksparse", meta, arrays)
+
+
 def main():
   tn = ref_shim.load()
   assert tn.__version__ == "0.4.6"
@@ -266,6 +307,7 @@ def main():
   gen_greedy(tn)
   gen_split(tn)
   gen_lanczos(tn)
+  gen_blocksparse(tn)
 
 
 if __name__ == "__main__":

@@ -48,6 +48,12 @@ def run(be, dtype, shape_a, shape_b, axes, reps=50, batch=None):
 
 if __name__ == "__main__":
   be = tb.get_backend()
+  if len(sys.argv) > 1 and sys.argv[1] == "--flagship":
+    # one batched flagship launch family only (used under ncu): 64 x [(1024 x 512) . (512 x 1024)]
+    dt = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+    run(be, dt, (64, 1024, 512), (64, 512, 1024), None, reps=3, batch=True)
+    run(be, dt, (512, 2, 512), (512, 2, 512), [[2], [0]], reps=3)
+    sys.exit(0)
   for dt in ("bf16", "f32", "f64"):
     run(be, dt, (512, 2, 512), (512, 2, 512), [[2], [0]])
     run(be, dt, (512, 2, 512), (512, 2, 512), [[0], [2]])
