@@ -1,0 +1,195 @@
+"""Multi-GPU execution of the contraction path: one process per GPU,
+`torch.distributed` (NCCL over NVLink 5 / NVSwitch) as the plumbing.
+
+The reference has no parallelism of any kind; what shards naturally is
+  (i)  independent networks / MPS batch samples  -> `shard_range`, `contract_independent`:
+       every rank contracts its own units, no data-path collective, one final all-gather of the
+       (tiny) results;
+  (ii) one network whose contraction *tree* fans out -> `partition_tree`, `contract_tree_parallel`:
+       the pairwise path (contractors/opt_einsum_paths/path_contractors.py:87-90 executes it as a
+       sequential list) is a binary tree; disjoint subtrees are independent.  The tree is cut into
+       subtrees weighted by 2MNK, packed onto ranks longest-processing-time first, and each subtree
+       result that is consumed on another rank is moved once, point-to-point (`dist.send/recv`, i.e.
+       NCCL p2p over NVLink), at the join.  Steps above the cut run on the rank that already holds
+       the larger operand.
+A single pairwise contraction is never split across GPUs (1 GFLOP problems do not amortise a
+collective), and the DMRG sweep is serial in the site index (dmrg.py:524-547): "replicas only".
+"""
+import numpy as np
+
+
+def shard_range(n_units, rank, world):
+  """contiguous, balanced shard of `n_units` independent units for `rank`."""
+  base, rem = divmod(n_units, world)
+  start = rank * base + min(rank, rem)
+  return range(start, start + base + (1 if rank < rem else 0))
+
+
+def contract_independent(units, contract_fn, rank, world, gather=None):
+  """Each rank runs `contract_fn(unit)` on its shard; `gather(list_of_local_results)` (e.g.
+  dist.all_gather_object) returns the per-rank lists.  Results come back in unit order."""
+  mine = [contract_fn(units[i]) for i in shard_range(len(units), rank, world)]
+  if gather is None or world == 1:
+    return mine
+  parts = gather(mine)
+  return [r for part in parts for r in part]
+
+
+# ----------------------------------------------------------------------- contraction tree
+def path_to_ssa(n_inputs, path):
+  """opt_einsum 'linear' path -> SSA triples (id_a, id_b, id_out)."""
+  ids = list(range(n_inputs))
+  nxt = n_inputs
+  out = []
+  for a, b in path:
+    ia, ib = ids[a], ids[b]
+    for i in sorted([a, b], reverse=True):
+      del ids[i]
+    ids.append(nxt)
+    out.append((ia, ib, nxt))
+    nxt += 1
+  return out
+
+
+def partition_tree(n_inputs, path, step_flops, world, oversub=4):
+  """Assign every pairwise step of `path` to a rank.
+
+  Returns (owner, transfers, info): owner[s] = rank executing SSA step s (in path order);
+  transfers = list of (tensor_id, src_rank, dst_rank, before_step) point-to-point moves;
+  info = dict(total, per_rank, critical) flop accounting (speed-up bound = total / critical)."""
+  ssa = path_to_ssa(n_inputs, path)
+  producer = {o: i for i, (_, _, o) in enumerate(ssa)}       # tensor id -> step index
+  cost = {}                                                  # subtree flops per tensor id
+
+  def subtree_cost(t):
+    if t < n_inputs:
+      return 0.0
+    if t not in cost:
+      a, b, _ = ssa[producer[t]]
+      cost[t] = step_flops[producer[t]] + subtree_cost(a) + subtree_cost(b)
+    return cost[t]
+  root = ssa[-1][2] if ssa else 0
+  total = subtree_cost(root)
+  # grow a frontier of independent subtrees by repeatedly splitting the most expensive one
+  frontier = [root]
+  target = max(1, world * oversub)
+  def splittable(t):
+    a, b, _ = ssa[producer[t]]
+    return a >= n_inputs or b >= n_inputs       # a step on two inputs is a leaf of the cut
+  while len(frontier) < target:
+    cand = [t for t in frontier if t >= n_inputs and splittable(t)]
+    if not cand:
+      break
+    t = max(cand, key=subtree_cost)
+    if subtree_cost(t) < total / (8.0 * target):
+      break
+    a, b, _ = ssa[producer[t]]
+    frontier.remove(t)
+    frontier.extend([x for x in (a, b) if x >= n_inputs])   # inputs live on every rank
+  # longest-processing-time-first packing of the frontier subtrees
+  load = [0.0] * world
+  tensor_rank = {}
+  for t in sorted(frontier, key=subtree_cost, reverse=True):
+    r = int(np.argmin(load))
+    load[r] += subtree_cost(t)
+    tensor_rank[t] = r
+
+  owner = [None] * len(ssa)
+
+  def assign_subtree(t, r):
+    if t < n_inputs:
+      return
+    s = producer[t]
+    owner[s] = r
+    a, b, _ = ssa[s]
+    assign_subtree(a, r)
+    assign_subtree(b, r)
+  for t, r in tensor_rank.items():
+    assign_subtree(t, r)
+  # steps above the cut: run where the larger-cost operand already lives
+  transfers = []
+  where = dict(tensor_rank)
+
+  def locate(t):
+    if t in where:
+      return where[t]
+    if t < n_inputs:
+      return None                                            # inputs are available on every rank
+    s = producer[t]
+    if owner[s] is not None:
+      where[t] = owner[s]
+      return owner[s]
+    a, b, _ = ssa[s]
+    ra, rb = locate(a), locate(b)
+    if ra is None and rb is None:
+      r = int(np.argmin(load))
+    elif ra is None:
+      r = rb
+    elif rb is None:
+      r = ra
+    else:
+      r = ra if subtree_cost(a) >= subtree_cost(b) else rb
+    owner[s] = r
+    load[r] += step_flops[s]
+    for x, rx in ((a, ra), (b, rb)):
+      if rx is not None and rx != r:
+        transfers.append((x, rx, r, s))
+    where[t] = r
+    return r
+  locate(root)
+  for s in range(len(ssa)):
+    if owner[s] is None:
+      owner[s] = 0
+  # critical path (flops) through the tree = lower bound on any schedule
+  crit = {}
+
+  def critical(t):
+    if t < n_inputs:
+      return 0.0
+    if t not in crit:
+      a, b, _ = ssa[producer[t]]
+      crit[t] = step_flops[producer[t]] + max(critical(a), critical(b))
+    return crit[t]
+  info = dict(total=total, per_rank=load, critical=critical(root), root_rank=where.get(root, 0))
+  return owner, sorted(transfers, key=lambda x: x[3]), info
+
+
+def contract_tree_parallel(tensors, labels, out_labels, path, rank, world, contract_pair, send, recv,
+                           step_flops=None):
+  """Execute `path` with the steps spread over `world` ranks.
+
+  contract_pair(t1, labels1, t2, labels2) -> (tensor, labels)   (contract_between semantics)
+  send(tensor, dst) / recv(shape_labels_hint, src) -> tensor     (NCCL / gloo point-to-point)
+  Every rank holds all inputs.  Returns (result or None, root_rank)."""
+  n = len(tensors)
+  ssa = path_to_ssa(n, path)
+  if step_flops is None:
+    step_flops = [1.0] * len(ssa)
+  owner, transfers, info = partition_tree(n, path, step_flops, world)
+  vals = {i: (tensors[i], list(labels[i])) for i in range(n)}
+  pending = {}
+  for t, src, dst, before in transfers:
+    pending.setdefault(before, []).append((t, src, dst))
+  # labels of every intermediate are needed on the receiving side: replay them symbolically
+  lab = {i: list(labels[i]) for i in range(n)}
+  for a, b, o in ssa:
+    shared = [l for l in lab[a] if l in lab[b]]
+    lab[o] = [l for l in lab[a] if l not in shared] + [l for l in lab[b] if l not in shared]
+  for s, (a, b, o) in enumerate(ssa):
+    for t, src, dst in pending.get(s, []):
+      if rank == src:
+        send(vals[t][0], dst)
+      elif rank == dst:
+        vals[t] = (recv(t, src), lab[t])
+    if owner[s] == rank:
+      ta, la = vals[a]
+      tb, lb = vals[b]
+      vals[o] = contract_pair(ta, la, tb, lb)
+      # free operands that are intermediates
+      for x in (a, b):
+        if x >= n:
+          vals.pop(x, None)
+  root = ssa[-1][2] if ssa else 0
+  root_rank = owner[-1] if ssa else 0
+  res = vals.get(root, (None, None))[0] if rank == root_rank else None
+  return res, root_rank, info

@@ -1,0 +1,225 @@
+"""TEST DOUBLE for libtnb200.so — lets the *host logic* of the cuda_b200 adapter (registration in the
+reference's backend factory, axes bookkeeping, views, dtype promotion, error translation, Lanczos /
+split control flow) run in the GPU-less build container against the REAL reference callers
+(`tn.Node`, `tn.ncon`, `contractors.greedy`, `split_node*`, `FiniteDMRG`).
+
+It implements the C-ABI entry points of include/tnb200.h on HOST memory with the numpy oracle.  It lives
+under tests/ and is never importable from the product package; the product has no CPU path."""
+import ctypes
+import numpy as np
+from oracle import np_backend as nb
+
+_NP = {0: np.float64, 1: np.float32, 2: np.float16, 4: np.complex64, 5: np.complex128, 6: np.int32, 7: np.int64}
+
+
+def _desc(arg):
+  return arg._obj if hasattr(arg, "_obj") else arg
+
+
+def _view(arg):
+  d = _desc(arg)
+  dt = np.dtype(_NP[d.dtype])
+  nd = d.ndim
+  shape = tuple(d.shape[i] for i in range(nd))
+  strides = tuple(d.stride[i] * dt.itemsize for i in range(nd))
+  if any(s == 0 for s in shape):
+    return np.zeros(shape, dtype=dt)
+  span = sum((s - 1) * abs(st) for s, st in zip(shape, strides)) + dt.itemsize
+  buf = (ctypes.c_char * span).from_address(d.data)
+  return np.ndarray(shape, dtype=dt, buffer=buf, strides=strides)
+
+
+def _scalar_at(ptr, code):
+  dt = np.dtype(_NP[code])
+  return np.ndarray((), dtype=dt, buffer=(ctypes.c_char * dt.itemsize).from_address(ptr))
+
+
+class FakeLib:
+  """same callables as the ctypes library object"""
+
+  def __init__(self):
+    self._err = b""
+    self._kernel = b"fake"
+    self._launches = 0
+
+  def _fail(self, code, msg):
+    self._err = msg.encode()
+    return code
+
+  def tnb200_last_error(self):
+    return self._err
+
+  def tnb200_last_kernel(self):
+    return self._kernel
+
+  def tnb200_abi_version(self):
+    return 1
+
+  def tnb200_launch_count(self):
+    return self._launches
+
+  def tnb200_tensordot(self, a, b, c, naxes, axes_a, axes_b, nbatch, batch_a, batch_b, flags, stream):
+    A, B, C = _view(a), _view(b), _view(c)
+    ax_a = [axes_a[i] for i in range(naxes)]
+    ax_b = [axes_b[i] for i in range(naxes)]
+    ba = [batch_a[i] for i in range(nbatch)]
+    bb = [batch_b[i] for i in range(nbatch)]
+    for x, y in zip(ax_a, ax_b):
+      if A.shape[x] != B.shape[y]:
+        return self._fail(-1, "shape-mismatch for sum")
+    if flags & 1:
+      A = np.conj(A)
+    if flags & 2:
+      B = np.conj(B)
+    self._launches += 1
+    if nbatch == 0:
+      C[...] = np.tensordot(A, B, (ax_a, ax_b))
+      return 0
+    fa = [i for i in range(A.ndim) if i not in ax_a and i not in ba]
+    fb = [i for i in range(B.ndim) if i not in ax_b and i not in bb]
+    L = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOP"
+    sa, sb = [None] * A.ndim, [None] * B.ndim
+    n = 0
+    for x, y in zip(ba, bb):
+      sa[x] = sb[y] = L[n]; n += 1
+    for x, y in zip(ax_a, ax_b):
+      sa[x] = sb[y] = L[n]; n += 1
+    for x in fa:
+      sa[x] = L[n]; n += 1
+    for y in fb:
+      sb[y] = L[n]; n += 1
+    out = "".join(sa[x] for x in ba) + "".join(sa[x] for x in fa) + "".join(sb[y] for y in fb)
+    C[...] = np.einsum("".join(sa) + "," + "".join(sb) + "->" + out, A, B)
+    return 0
+
+  def tnb200_copy(self, src, dst, conj, stream):
+    s, d = _view(src), _view(dst)
+    self._launches += 1
+    if np.iscomplexobj(s) and not np.iscomplexobj(d):
+      s = s.real
+    d[...] = np.conj(s) if conj else s
+    return 0
+
+  def tnb200_binary(self, op, a, b, c, stream):
+    A, B, C = _view(a), _view(b), _view(c)
+    self._launches += 1
+    with np.errstate(all="ignore"):
+      C[...] = [np.add, np.subtract, np.multiply, np.divide, np.power][op](A, B)
+    return 0
+
+  def tnb200_unary(self, op, a, c, stream):
+    A, C = _view(a), _view(c)
+    self._launches += 1
+    f = [np.conj, np.sqrt, np.abs, np.negative, np.exp, np.log, np.sin, np.cos, np.sign, np.real, np.imag][op]
+    with np.errstate(all="ignore"):
+      C[...] = f(A)
+    return 0
+
+  def tnb200_affine_inplace(self, x, ar, ai, br, bi, stream):
+    X = _view(x)
+    self._launches += 1
+    if np.iscomplexobj(X):
+      X[...] = X * complex(ar, ai) + complex(br, bi)
+    else:
+      X[...] = X * ar + br
+    return 0
+
+  def tnb200_scale_by_device_scalar(self, x, alpha_ptr, alpha_dtype, power, stream):
+    X = _view(x)
+    s = _scalar_at(alpha_ptr, alpha_dtype)[()]
+    self._launches += 1
+    if not np.iscomplexobj(X):
+      s = np.real(s)
+    X[...] = X / s if power < 0 else X * s
+    return 0
+
+  def tnb200_axpy(self, x, y, ar, ai, alpha_ptr, sign, stream):
+    X, Y = _view(x), _view(y)
+    self._launches += 1
+    if alpha_ptr:
+      alpha = sign * _scalar_at(alpha_ptr, _desc(x).dtype)[()]
+    else:
+      alpha = complex(ar, ai) if np.iscomplexobj(X) else ar
+    Y[...] = Y + alpha * X
+    return 0
+
+  def tnb200_fill(self, c, re, im, stream):
+    C = _view(c)
+    self._launches += 1
+    C[...] = complex(re, im) if np.iscomplexobj(C) else re
+    return 0
+
+  def tnb200_eye(self, c, k, stream):
+    C = _view(c)
+    C[...] = np.eye(C.shape[0], C.shape[1], k=k, dtype=C.dtype)
+    return 0
+
+  def tnb200_randn(self, c, seed, stream):
+    C = _view(c)
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal(C.shape)
+    if np.iscomplexobj(C):
+      v = v + 1j * rng.standard_normal(C.shape)
+    C[...] = v
+    return 0
+
+  def tnb200_uniform(self, c, lo, hi, seed, stream):
+    C = _view(c)
+    rng = np.random.default_rng(seed)
+    v = rng.uniform(lo, hi, C.shape)
+    if np.iscomplexobj(C):
+      v = v + 1j * rng.uniform(lo, hi, C.shape)
+    C[...] = v
+    return 0
+
+  def tnb200_norm(self, a, out, stream):
+    A = _view(a)
+    code = {5: 0, 4: 1}.get(_desc(a).dtype, _desc(a).dtype)
+    _scalar_at(out, code)[...] = np.linalg.norm(A)
+    return 0
+
+  def tnb200_dot(self, x, y, conj_x, out, stream):
+    X, Y = _view(x), _view(y)
+    v = np.sum((np.conj(X) if conj_x else X) * Y)
+    _scalar_at(out, _desc(x).dtype)[...] = v
+    return 0
+
+  def tnb200_sum(self, a, c, naxes, axes, stream):
+    A, C = _view(a), _view(c)
+    C[...] = np.sum(A, axis=tuple(axes[i] for i in range(naxes)))
+    return 0
+
+  def tnb200_trace(self, a, c, offset, axis1, axis2, stream):
+    A, C = _view(a), _view(c)
+    C[...] = np.trace(A, offset=offset, axis1=axis1, axis2=axis2)
+    return 0
+
+  def tnb200_diagflat(self, a, c, k, stream):
+    A, C = _view(a), _view(c)
+    C[...] = np.diagflat(A, k=k)
+    return 0
+
+  def tnb200_svd(self, a, u, s, vh, info, stream):
+    A = _view(a)
+    U, S, Vh = np.linalg.svd(A, full_matrices=False)
+    _view(u)[...] = U
+    _view(s)[...] = S
+    _view(vh)[...] = Vh
+    return 0
+
+  def tnb200_svd_truncation_count(self, s, max_sv, use_err, max_err, relative, keep_ptr, stream):
+    S = _view(s)
+    keep = nb.truncation_count(S, None if max_sv < 0 else max_sv, max_err if use_err else None, bool(relative))
+    np.ndarray((), dtype=np.int64, buffer=(ctypes.c_char * 8).from_address(keep_ptr))[...] = keep
+    return 0
+
+  def tnb200_qr(self, a, q, r, nonneg, stream):
+    A = _view(a)
+    Q, R = np.linalg.qr(A)
+    if nonneg:
+      ph = np.sign(np.diagonal(R))
+      Q = Q * ph
+      R = ph.conj()[:, None] * R
+    _view(q)[...] = Q
+    _view(r)[...] = R
+    return 0
