@@ -23,9 +23,19 @@ struct SimtParams {
   DevModes mK;  // summed modes: s0 = A, s1 = B
   int64_t M, N, K, batch;
   int conjA, conjB, a_kfast, b_nfast;
+  int ksplit;          // > 1: grid.y K-chunks accumulate atomically into `acc_ws` ([batch, M, N] of Acc)
+  int64_t kchunk;
+  void* acc_ws;
 };
 
 constexpr int SBM = 64, SBN = 64, SBK = 16;
+
+__device__ inline void atomic_acc(double* p, double v) { atomicAdd(p, v); }
+__device__ inline void atomic_acc(float* p, float v) { atomicAdd(p, v); }
+__device__ inline void atomic_acc(int32_t* p, int32_t v) { atomicAdd(p, v); }
+__device__ inline void atomic_acc(long long* p, long long v) { atomicAdd((unsigned long long*)p, (unsigned long long)v); }
+__device__ inline void atomic_acc(cuFloatComplex* p, cuFloatComplex v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
+__device__ inline void atomic_acc(cuDoubleComplex* p, cuDoubleComplex v) { atomicAdd(&p->x, v.x); atomicAdd(&p->y, v.y); }
 
 template <typename T, typename Acc>
 __global__ void __launch_bounds__(256) tensordot_simt_kernel(const __grid_constant__ SimtParams<T> p) {
@@ -59,12 +69,14 @@ __global__ void __launch_bounds__(256) tensordot_simt_kernel(const __grid_consta
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = acc_zero((Acc*)nullptr);
 
-  for (int64_t k0 = 0; k0 < p.K; k0 += SBK) {
+  const int64_t kbeg = p.ksplit > 1 ? (int64_t)blockIdx.y * p.kchunk : 0;
+  const int64_t kend = p.ksplit > 1 ? (kbeg + p.kchunk < p.K ? kbeg + p.kchunk : p.K) : p.K;
+  for (int64_t k0 = kbeg; k0 < kend; k0 += SBK) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       Acc v = acc_zero((Acc*)nullptr);
       int64_t k = k0 + ak[i];
-      if (aval[i] && k < p.K) {
+      if (aval[i] && k < kend) {
         int64_t ko, ko1;
         if (p.mK.n <= 1) ko = k * p.mK.s0[0]; else mode_offsets(p.mK, k, ko, ko1);
         v = to_acc(p.A[aoff[i] + ko]);
@@ -73,7 +85,7 @@ __global__ void __launch_bounds__(256) tensordot_simt_kernel(const __grid_consta
       As[ak[i]][am[i]] = v;
       Acc w = acc_zero((Acc*)nullptr);
       k = k0 + bk[i];
-      if (bval[i] && k < p.K) {
+      if (bval[i] && k < kend) {
         int64_t ko, ko1;
         if (p.mK.n <= 1) ko1 = k * p.mK.s1[0]; else mode_offsets(p.mK, k, ko, ko1);
         w = to_acc(p.B[boff[i] + ko1]);
@@ -106,8 +118,23 @@ __global__ void __launch_bounds__(256) tensordot_simt_kernel(const __grid_consta
       if (n >= p.N) continue;
       int64_t ob, ocn;
       mode_offsets(p.mN, n, ob, ocn);
-      p.C[offCb + ocm + ocn] = FromAcc<T, Acc>::f(acc[i][j]);
+      if (p.ksplit > 1) atomic_acc((Acc*)p.acc_ws + (bb * p.M + m) * p.N + n, acc[i][j]);
+      else p.C[offCb + ocm + ocn] = FromAcc<T, Acc>::f(acc[i][j]);
     }
+  }
+}
+
+// split-K epilogue: C[...] = convert(acc_ws[b, m, n])
+template <typename T, typename Acc>
+__global__ void splitk_finalize_kernel(const __grid_constant__ SimtParams<T> p) {
+  const int64_t total = p.batch * p.M * p.N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = i % p.N, t = i / p.N, m = t % p.M, bb = t / p.M;
+    int64_t oa, ob, oc, o1, ocm, o2, ocn;
+    mode_offsets3(p.mB, bb, oa, ob, oc);
+    mode_offsets(p.mM, m, o1, ocm);
+    mode_offsets(p.mN, n, o2, ocn);
+    p.C[oc + ocm + ocn] = FromAcc<T, Acc>::f(((const Acc*)p.acc_ws)[i]);
   }
 }
 
@@ -133,6 +160,32 @@ static int launch_simt(const void* A, const void* B, void* C, const ModeList& mB
   p.b_nfast = last_stride(mN, 0) <= last_stride(mK, 1);
   int64_t tiles = ((p.M + SBM - 1) / SBM) * ((p.N + SBN - 1) / SBN) * p.batch;
   TNB_REQUIRE(tiles < (1LL << 31), TNB200_ERR_UNSUPPORTED, "tensordot: output too large for one launch");
+  // split-K when the output is too small to fill the GPU but the contraction is long
+  p.ksplit = 1; p.kchunk = p.K; p.acc_ws = nullptr;
+  const int sms = num_sms();
+  if (tiles * 2 <= sms && p.K >= 2048) {
+    int64_t want = (2 * sms + tiles - 1) / tiles;
+    int64_t maxs = p.K / 512;
+    int64_t sp = want < maxs ? want : maxs;
+    if (sp > 1) {
+      p.kchunk = ((p.K + sp - 1) / sp + SBK - 1) / SBK * SBK;
+      p.ksplit = (int)((p.K + p.kchunk - 1) / p.kchunk);
+    }
+  }
+  if (p.ksplit > 1) {
+    size_t bytes = sizeof(Acc) * (size_t)(p.batch * p.M * p.N);
+    int rc = ws_alloc(&p.acc_ws, bytes, st);
+    if (rc) return rc;
+    TNB_CHECK_CUDA(cudaMemsetAsync(p.acc_ws, 0, bytes, st));
+    tensordot_simt_kernel<T, Acc><<<dim3((unsigned)tiles, (unsigned)p.ksplit), 256, 0, st>>>(p);
+    int64_t tot = p.batch * p.M * p.N;
+    int64_t fb = (tot + 255) / 256; if (fb > sms * 8) fb = sms * 8;
+    splitk_finalize_kernel<T, Acc><<<(unsigned)fb, 256, 0, st>>>(p);
+    TNB_LAUNCH_CHECK();
+    count_launch(2);
+    set_kernel_name("simt_splitk");
+    return ws_free(p.acc_ws, st);
+  }
   tensordot_simt_kernel<T, Acc><<<(unsigned)tiles, 256, 0, st>>>(p);
   TNB_LAUNCH_CHECK();
   count_launch();
@@ -186,7 +239,7 @@ static ModeList order_k(const ModeList& mK, int by) {
 // Pack a (batch, free, K) view of one operand into a contiguous row-major [batch, free, K]
 // scratch buffer with the strided-copy kernel (the only place a transpose is materialised).
 static int pack_operand(int dt, const void* src, const ModeList& mB, int wb, const ModeList& mF,
-                        const ModeList& mK, int wk, void** out, cudaStream_t st) {
+                        const ModeList& mK, int wk, void** out, int64_t* pitch, cudaStream_t st) {
   tnb200_tensor_t s, d;
   s.data = const_cast<void*>(src); s.dtype = dt; d.dtype = dt;
   int nd = 0;
@@ -204,8 +257,23 @@ static int pack_operand(int dt, const void* src, const ModeList& mB, int wb, con
     return TNB200_ERR_UNSUPPORTED;
   }
   s.ndim = d.ndim = nd;
+  // contiguous [batch, free, K] with the K row padded to a 16-byte multiple (`pitch` elements)
+  int64_t ktot = mK.total(), ftot = mF.total();
+  const int64_t per16 = 16 / dtype_size(dt) > 0 ? 16 / dtype_size(dt) : 1;
+  const int64_t kp = (ktot + per16 - 1) / per16 * per16;
+  *pitch = kp;
   int64_t tot = 1;
-  for (int i = nd - 1; i >= 0; --i) { d.shape[i] = s.shape[i]; d.stride[i] = tot; tot *= s.shape[i]; }
+  {
+    // strides of the destination modes: K modes contiguous, free modes over the padded pitch
+    int idx = nd - 1;
+    int64_t st_ = 1;
+    for (int i = mK.n - 1; i >= 0; --i, --idx) { d.shape[idx] = s.shape[idx]; d.stride[idx] = st_; st_ *= s.shape[idx]; }
+    st_ = kp;
+    for (int i = mF.n - 1; i >= 0; --i, --idx) { d.shape[idx] = s.shape[idx]; d.stride[idx] = st_; st_ *= s.shape[idx]; }
+    st_ = kp * ftot;
+    for (int i = mB.n - 1; i >= 0; --i, --idx) { d.shape[idx] = s.shape[idx]; d.stride[idx] = st_; st_ *= s.shape[idx]; }
+    tot = kp * ftot * mB.total();
+  }
   int rc = ws_alloc(out, (size_t)tot * dtype_size(dt), st);
   if (rc) return rc;
   d.data = *out;
@@ -286,7 +354,8 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
   const bool gemm_dtype = dt == TNB200_F64 || dt == TNB200_F32 || dt == TNB200_F16 || dt == TNB200_BF16;
   const bool want_gemm = gemm_dtype && math != (TNB200_MATH_SIMT >> 4) &&
                          !(dt == TNB200_F32 && math == (TNB200_MATH_STRICT >> 4)) &&
-                         (double)M * (double)N * (double)K * (double)Bt >= 32768.0 && gB.n <= 1;
+                         (double)M * (double)N * (double)K * (double)Bt >= 32768.0 && gB.n <= 1 &&
+                         !(M <= 64 && N <= 64 && Bt * 2 <= num_sms() && K >= 8192);   // skinny, long K: split-K SIMT
   if (want_gemm) {
     int64_t cm_ext, cm_s, cn_ext, cn_s;
     ModeList cM, cN;
@@ -332,14 +401,16 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
         void *packA = nullptr, *packB = nullptr;
         int rc = 0;
         if (!bestA) {   // repack A as a contiguous K-major [batch, M, K] matrix (k in the common order)
-          rc = pack_operand(dt, a->data, gB, 0, gM, ko, 0, &packA, st);
-          va = OperandView(); va.ptr = packA; va.nF = 1; va.fe[0] = M; va.fs[0] = K; va.nK = 1; va.ke[0] = K; va.ks[0] = 1; va.sb = M * K;
+          int64_t kp = K;
+          rc = pack_operand(dt, a->data, gB, 0, gM, ko, 0, &packA, &kp, st);
+          va = OperandView(); va.ptr = packA; va.nF = 1; va.fe[0] = M; va.fs[0] = kp; va.nK = 1; va.ke[0] = K; va.ks[0] = 1; va.sb = M * kp;
         }
         if (rc == 0 && !bestB) {
           ModeList nB;  // free modes of B with B strides in slot 0
           for (int i = 0; i < gN.n; ++i) nB.push(gN.ext[i], gN.s0[i]);
-          rc = pack_operand(dt, b->data, gB, 1, nB, ko, 1, &packB, st);
-          vb = OperandView(); vb.ptr = packB; vb.nF = 1; vb.fe[0] = N; vb.fs[0] = K; vb.nK = 1; vb.ke[0] = K; vb.ks[0] = 1; vb.sb = N * K;
+          int64_t kp = K;
+          rc = pack_operand(dt, b->data, gB, 1, nB, ko, 1, &packB, &kp, st);
+          vb = OperandView(); vb.ptr = packB; vb.nF = 1; vb.fe[0] = N; vb.fs[0] = kp; vb.nK = 1; vb.ke[0] = K; vb.ks[0] = 1; vb.sb = N * kp;
         }
         if (rc == 0) {
           // a packed operand still contracts over ALL of K with one stride: collapse the other
@@ -358,14 +429,16 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
           if (rc == TNB200_ERR_UNSUPPORTED && (bestA || bestB) && !(packA && packB)) {
             // in-place addressing was rejected at encode time (tile-size dependent): repack everything
             if (!packA) {
-              rc = pack_operand(dt, a->data, gB, 0, gM, ko, 0, &packA, st);
-              va = OperandView(); va.ptr = packA; va.nF = 1; va.fe[0] = M; va.fs[0] = K; va.nK = 1; va.ke[0] = K; va.ks[0] = 1; va.sb = M * K;
+              int64_t kp = K;
+              rc = pack_operand(dt, a->data, gB, 0, gM, ko, 0, &packA, &kp, st);
+              va = OperandView(); va.ptr = packA; va.nF = 1; va.fe[0] = M; va.fs[0] = kp; va.nK = 1; va.ke[0] = K; va.ks[0] = 1; va.sb = M * kp;
             } else { va.nK = 1; va.ke[0] = K; va.ks[0] = 1; }
             if ((rc == 0 || rc == TNB200_ERR_UNSUPPORTED) && !packB) {
               ModeList nB;
               for (int i = 0; i < gN.n; ++i) nB.push(gN.ext[i], gN.s0[i]);
-              rc = pack_operand(dt, b->data, gB, 1, nB, ko, 1, &packB, st);
-              vb = OperandView(); vb.ptr = packB; vb.nF = 1; vb.fe[0] = N; vb.fs[0] = K; vb.nK = 1; vb.ke[0] = K; vb.ks[0] = 1; vb.sb = N * K;
+              int64_t kp = K;
+              rc = pack_operand(dt, b->data, gB, 1, nB, ko, 1, &packB, &kp, st);
+              vb = OperandView(); vb.ptr = packB; vb.nF = 1; vb.fe[0] = N; vb.fs[0] = kp; vb.nK = 1; vb.ke[0] = K; vb.ks[0] = 1; vb.sb = N * kp;
             } else if (packB) { vb.nK = 1; vb.ke[0] = K; vb.ks[0] = 1; }
             if (rc == 0) { g.A = va; g.B = vb; rc = (dt == TNB200_F64) ? gemm_dmma_f64(g, st) : gemm_tcgen05(g, st); }
           }

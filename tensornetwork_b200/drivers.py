@@ -222,6 +222,60 @@ def execute_plan(backend, tensors, steps, result_slot):
   return vals[result_slot]
 
 
+def execute_plan_streams(backend, tensors, steps, result_slot, streams):
+  """Dependency-aware execution of a plan on several CUDA streams: every step runs on the stream
+  of its most recently produced operand and waits (event) only for operands produced elsewhere,
+  so independent branches of the contraction tree overlap.  Used under CUDA-graph capture, where
+  the stream/event structure becomes the graph's dependency edges.  Returns (result, all values)."""
+  torch = backend.torch
+  main = torch.cuda.current_stream()
+  vals = list(tensors)
+  home = [None] * len(vals)            # stream index that produced each slot (None: graph input)
+  events = {}
+  for s in streams:
+    s.wait_stream(main)
+  rr = 0
+  for st in steps:
+    op = st[0]
+    ins = [st[1], st[2]] if op in ("tensordot", "batched") else [st[1]]
+    out_slot = len(vals)
+    produced = [i for i in ins if home[i] is not None]
+    if op == "transpose":              # a view: no kernel, inherits its operand's stream
+      vals.append(backend.transpose(vals[st[1]], st[2]))
+      home.append(home[st[1]])
+      if st[1] in events:
+        events[out_slot] = events[st[1]]
+      continue
+    if not produced:
+      si = rr % len(streams)
+      rr += 1
+    else:
+      si = home[max(produced)]
+    stream = streams[si]
+    for i in produced:
+      if home[i] != si:
+        stream.wait_event(events[i])
+    with torch.cuda.stream(stream):
+      if op == "tensordot":
+        vals.append(backend.tensordot(vals[st[1]], vals[st[2]], (st[3], st[4])))
+      elif op == "batched":
+        vals.append(backend._contract(vals[st[1]], vals[st[2]], list(st[3]), list(st[4]),  # pylint: disable=protected-access
+                                      list(st[5]), list(st[6])))
+      elif op == "ptrace":
+        vals.append(backend.trace(backend.reshape(backend.transpose(vals[st[1]], st[2]), st[3])))
+      elif op == "sum":
+        vals.append(backend.sum(vals[st[1]], st[2]))
+      else:
+        raise RuntimeError("unknown plan step " + str(op))
+      e = torch.cuda.Event()
+      e.record(stream)
+      events[out_slot] = e
+    home.append(si)
+  for s in streams:
+    main.wait_stream(s)
+  return vals[result_slot], vals
+
+
 def ncon(tensors, network_structure, con_order=None, out_order=None, backend=None):
   """Same call signature / semantics as `tn.ncon` (ncon_interface.py:523) for backend tensors
   or numpy arrays (converted with `convert_to_tensor`, i.e. copied host->device)."""
@@ -319,7 +373,7 @@ class CompiledNetwork:
   overwritten by the next call (clone it to keep it)."""
 
   def __init__(self, backend, shapes, dtype, labels, out_labels=(), path=None, nbatch=0,
-               algorithm=None):
+               algorithm=None, num_streams=4):
     from . import tensor as T  # pylint: disable=import-outside-toplevel
     self.backend = backend
     self.nbatch = nbatch
@@ -344,9 +398,15 @@ class CompiledNetwork:
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     self.graph = torch.cuda.CUDAGraph()
+    self.streams = [torch.cuda.Stream() for _ in range(max(1, num_streams))]
     l0 = backend.lib.tnb200_launch_count()
     with torch.cuda.graph(self.graph):
-      self.output = execute_plan(backend, self.inputs, self.steps, self.res_slot)
+      if num_streams > 1:
+        # keep every intermediate alive until capture ends: no buffer is recycled across streams
+        self.output, self._keep = execute_plan_streams(backend, self.inputs, self.steps, self.res_slot,
+                                                       self.streams)
+      else:
+        self.output = execute_plan(backend, self.inputs, self.steps, self.res_slot)
     self.launches_per_replay = int(backend.lib.tnb200_launch_count() - l0)
 
   def load(self, tensors):

@@ -138,3 +138,19 @@ def test_strict_fp32_mode_is_true_fp32():
   finally:
     be.math_mode = old
   assert_close(out, np.tensordot(a.astype(np.float64), b.astype(np.float64), ([2], [0])), tol=2e-5)
+
+
+def test_skinny_long_k_uses_split_k():
+  """(M, N tiny; K huge) — the closing step of the cfg-2 greedy path is (2 x 262144) . (262144 x 2)."""
+  be = get_backend()
+  rng = np.random.default_rng(6)
+  for dtype, tol in (("float64", 1e-10), ("float32", 2e-5)):
+    a = rng.standard_normal((2, 262144)).astype(dtype)
+    b = rng.standard_normal((262144, 2)).astype(dtype)
+    out = be.tensordot(be.convert_to_tensor(a), be.convert_to_tensor(b), 1)
+    assert be.lib.tnb200_last_kernel().decode() == "simt_splitk"
+    assert_close(out, a.astype(np.float64) @ b.astype(np.float64), tol=tol)
+  x = rng.standard_normal((3, 5, 40000))
+  y = rng.standard_normal((40000, 5, 7))
+  assert_close(be.tensordot(be.convert_to_tensor(x), be.convert_to_tensor(y), ([2, 1], [0, 1])),
+               np.tensordot(x, y, ([2, 1], [0, 1])), tol=1e-10)
