@@ -214,7 +214,7 @@ def main():
   bytes_step = NB * sum((m * k + k * n + m * n) * esize for m, k, n in work)
   h2d_bytes = sum(h.numel() * esize for h in host)
 
-  net = drivers.CompiledNetwork(be, [tuple(h.shape) for h in host], args.dtype if args.dtype != "bf16" else "bfloat16",
+  net = drivers.CompiledNetwork(be, [tuple(h.shape) for h in host], {"bf16": "bfloat16", "f32": np.float32, "f64": np.float64}[args.dtype],
                                 labels, [], path=path, nbatch=nbatch) if not args.no_graph else None
   dev = [tb.B200Tensor(h.to(be.device), code) for h in host]
   if net is not None:

@@ -306,6 +306,244 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// =====================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.
+// Each CTA stages its own 128 rows of A and HALF of the B tile (BN/2 columns); the MMA issued
+// by the leader CTA (cluster rank 0) reads both halves of B across the pair, so the per-CTA
+// L2->smem traffic per flop drops by 1.5x versus the 1-CTA 128 x 256 tile (the 1-CTA kernel
+// is L2-bandwidth bound on K=512 problems: profiles/r1_ncu_full_tcgen05_bf16_flagship_batch64_v1.csv).
+//   * TMA loads of both CTAs complete on the LEADER's full barrier (cta_group::2 + peer-bit mask);
+//   * tcgen05.commit multicasts the slot release / accumulator-ready signal to both CTAs;
+//   * both epilogues arrive (remotely for the peer) on the leader's tmem_empty barrier.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  const uint32_t leader_bar = bar & 0xFEFFFFFFu;   // peer bit cleared: transaction bytes land on CTA 0's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ TcParams p) {
+  constexpr int ES = KIND == 0 ? 2 : 4;
+  constexpr int BK = kRowBytes / ES;
+  constexpr int CHUNK = kRowBytes / ES;
+  constexpr int A_BYTES = kBM * kRowBytes;       // this CTA's 128 rows of A
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int BN = p.BN;                           // pair tile is 256 x BN
+  const int BNH = BN / 2;                        // this CTA's share of the B tile
+  const int B_BYTES = BNH * kRowBytes;
+  const int STAGE_BYTES = A_BYTES + B_BYTES;
+  const int S = p.stages;
+  uint64_t* bars = (uint64_t*)(smem + (size_t)S * STAGE_BYTES);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    // full: leader's expect_tx arrive + the peer's remote arrive; empty / tmem_full: one multicast commit;
+    // tmem_empty: 4 epilogue warps of each CTA
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_kb = p.num_kb;
+  const int64_t first = blockIdx.x >> 1, step = gridDim.x >> 1;   // pair index
+
+  if (warp == 0 && lane == 0) {
+    // ===================================================== TMA producer (both CTAs)
+    int s = 0; uint32_t ph = 0;
+    for (int64_t tile = first; tile < p.num_tiles; tile += step) {
+      int64_t t = tile;
+      const int ni = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int mi = (int)(t % p.tiles_m);
+      const int bi = (int)(t / p.tiles_m);
+      const int m0 = mi * 2 * kBM + (int)rank * kBM, n0 = ni * BN + (int)rank * BNH;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1);
+        if (leader) mbar_expect_tx(full_bar(s), (uint32_t)(2 * STAGE_BYTES));
+        else mbar_arrive_remote(full_bar(s), 0);
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+        const int k0 = kb * BK;
+        const int ak_in = p.a_ke ? (int)(k0 % p.a_ke) : k0, ak_out = p.a_ke ? (int)(k0 / p.a_ke) : 0;
+        const int bk_in = p.b_ke ? (int)(k0 % p.b_ke) : k0, bk_out = p.b_ke ? (int)(k0 / p.b_ke) : 0;
+        if (!p.a_mn) {
+          const int f_in = p.a_fe ? (int)(m0 % p.a_fe) : m0, f_out = p.a_fe ? (int)(m0 / p.a_fe) : 0;
+          tma_load_5d_2sm(sa, &tmA, full_bar(s), ak_in, f_in, f_out, ak_out, bi);
+        } else {
+#pragma unroll
+          for (int c = 0; c < kBM / CHUNK; ++c) {
+            const int f = m0 + c * CHUNK;
+            const int f_in = p.a_fe ? (int)(f % p.a_fe) : f, f_out = p.a_fe ? (int)(f / p.a_fe) : 0;
+            tma_load_5d_2sm(sa + c * (BK * kRowBytes), &tmA, full_bar(s), f_in, ak_in, ak_out, f_out, bi);
+          }
+        }
+        if (!p.b_mn) {
+          const int f_in = p.b_fe ? (int)(n0 % p.b_fe) : n0, f_out = p.b_fe ? (int)(n0 / p.b_fe) : 0;
+          tma_load_5d_2sm(sb, &tmB, full_bar(s), bk_in, f_in, f_out, bk_out, bi);
+        } else {
+          for (int c = 0; c < BNH / CHUNK; ++c) {
+            const int f = n0 + c * CHUNK;
+            const int f_in = p.b_fe ? (int)(f % p.b_fe) : f, f_out = p.b_fe ? (int)(f / p.b_fe) : 0;
+            tma_load_5d_2sm(sb + c * (BK * kRowBytes), &tmB, full_bar(s), f_in, bk_in, bk_out, f_out, bi);
+          }
+        }
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================================================== MMA issuer (leader CTA only)
+    const uint32_t a_layout = (p.a_mn && KIND == 1) ? 1u : 2u;
+    const uint32_t b_layout = (p.b_mn && KIND == 1) ? 1u : 2u;
+    const uint32_t a_lbo = p.a_mn ? BK * kRowBytes : 0u, b_lbo = p.b_mn ? BK * kRowBytes : 0u;
+    const uint32_t a_sbo = (p.a_mn && KIND == 1) ? 512u : 1024u;
+    const uint32_t b_sbo = (p.b_mn && KIND == 1) ? 512u : 1024u;
+    const uint32_t a_kstep = p.a_mn ? (32u / ES) * kRowBytes : 32u;
+    const uint32_t b_kstep = p.b_mn ? (32u / ES) * kRowBytes : 32u;
+    int s = 0; uint32_t ph = 0;
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int64_t tile = first; tile < p.num_tiles; tile += step) {
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, a_layout);
+          const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, b_layout);
+          tc_mma_2sm<KIND>(d_tmem, ad, bd, p.idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit_2sm(empty_bar(s));
+        if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(acc));
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (both CTAs: their own 128 rows)
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_ph = 0;
+    for (int64_t tile = first; tile < p.num_tiles; tile += step) {
+      int64_t t = tile;
+      const int ni = (int)(t % p.tiles_n); t /= p.tiles_n;
+      const int mi = (int)(t % p.tiles_m);
+      const int64_t bi = t / p.tiles_m;
+      const int64_t row = (int64_t)mi * 2 * kBM + (int64_t)rank * kBM + q * 32 + lane;
+      const int64_t n0 = (int64_t)ni * BN;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        tmem_ld32(taddr0 + j * 32, r);
+        const int64_t col0 = n0 + j * 32;
+        if (row < p.M && col0 < p.N) {
+          const int64_t off = bi * p.c_sb + row * p.c_sm + col0;
+          const int ncol = (p.N - col0) >= 32 ? 32 : (int)(p.N - col0);
+          if (p.out_kind == 2) {
+            float* dst = (float*)p.C + off;
+            if (ncol == 32 && p.vec_ok) {
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                ((float4*)dst)[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                                __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = __uint_as_float(r[c]);
+            }
+          } else {
+            uint16_t* dst = (uint16_t*)p.C + off;
+            uint32_t pk[16];
+#pragma unroll
+            for (int v = 0; v < 16; ++v) {
+              float lo = __uint_as_float(r[2 * v]), hi = __uint_as_float(r[2 * v + 1]);
+              if (p.out_kind == 0) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); pk[v] = *(uint32_t*)&h; }
+              else { __half2 h = __floats2half2_rn(lo, hi); pk[v] = *(uint32_t*)&h; }
+            }
+            if (ncol == 32 && p.vec_ok) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v) ((uint4*)dst)[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = (uint16_t)(pk[c >> 1] >> ((c & 1) * 16));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // no CTA may exit (or free TMEM) while its peer can still signal it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -455,14 +693,25 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
       if (tiles >= sms || bn == 64) { BN = bn; break; }
     }
   }
+  // 2-CTA pairs (256 x BN tiles) for problems large enough to fill the GPU with pair tiles
+  static int force2 = -2;
+  if (force2 == -2) { const char* e = getenv("TNB200_2CTA"); force2 = e ? (e[0] == '0' ? 0 : 1) : -1; }
+  bool use2 = false;
+  if (g.M >= 256 && BN >= 128) {
+    const int64_t pair_tiles = ((g.M + 2 * kBM - 1) / (2 * kBM)) * ((g.N + BN - 1) / BN) * g.batch;
+    use2 = force2 == 1 || (force2 == -1 && BN == 256 && pair_tiles >= sms / 2);
+  }
+  if (force2 == 0) use2 = false;
   TcParams p;
   p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
   p.BN = BN;
   const int bk = kRowBytes / es;
   p.num_kb = (int)((g.K + bk - 1) / bk);
-  p.tiles_m = tiles_m; p.tiles_n = (g.N + BN - 1) / BN;
+  p.tiles_m = use2 ? (g.M + 2 * kBM - 1) / (2 * kBM) : tiles_m;
+  p.tiles_n = (g.N + BN - 1) / BN;
   p.num_tiles = p.tiles_m * p.tiles_n * g.batch;
-  const int stage_bytes = kBM * kRowBytes + BN * kRowBytes;
+  const int b_rows = use2 ? BN / 2 : BN;                   // B rows staged per CTA per k-block
+  const int stage_bytes = kBM * kRowBytes + b_rows * kRowBytes;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.num_kb + 1 && p.num_tiles <= sms) stages = p.num_kb + 1 > 2 ? p.num_kb + 1 : 2;
@@ -474,29 +723,40 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
   bool a_mn = false, b_mn = false;
   int rc = encode_operand(&tmA, g.dtype, g.A, g.M, g.K, g.batch, kBM, a_mn, p.a_fe, p.a_ke);
   if (rc) return rc;
-  rc = encode_operand(&tmB, g.dtype, g.B, g.N, g.K, g.batch, BN, b_mn, p.b_fe, p.b_ke);
+  rc = encode_operand(&tmB, g.dtype, g.B, g.N, g.K, g.batch, b_rows, b_mn, p.b_fe, p.b_ke);
   if (rc) return rc;
   p.a_mn = a_mn; p.b_mn = b_mn;
   // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B format, majors, N>>3, M>>4
   const uint32_t fmt = g.dtype == TNB200_BF16 ? 1u : (g.dtype == TNB200_F16 ? 0u : 2u);
+  const uint32_t mma_m = use2 ? 256u : 128u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+            ((uint32_t)(BN >> 3) << 17) | ((mma_m >> 4) << 24);
   const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
-  const int64_t grid = p.num_tiles < sms ? p.num_tiles : sms;
-  static bool attr_set[2] = {false, false};
   const int kind = g.dtype == TNB200_F32 ? 1 : 0;
-  if (!attr_set[kind]) {
-    cudaError_t e = kind == 0
-        ? cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-        : cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  static bool attr_set[4] = {false, false, false, false};
+  const int ai = kind + (use2 ? 2 : 0);
+  if (!attr_set[ai]) {
+    cudaError_t e;
+    if (!use2) e = kind == 0 ? cudaFuncSetAttribute(gemm_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                             : cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    else e = kind == 0 ? cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                       : cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("tcgen05: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return TNB200_ERR_CUDA; }
-    attr_set[kind] = true;
+    attr_set[ai] = true;
   }
-  if (kind == 0) gemm_tcgen05_kernel<0><<<(unsigned)grid, kThreads, smem, st>>>(tmA, tmB, p);
-  else gemm_tcgen05_kernel<1><<<(unsigned)grid, kThreads, smem, st>>>(tmA, tmB, p);
+  if (!use2) {
+    const int64_t grid = p.num_tiles < sms ? p.num_tiles : sms;
+    if (kind == 0) gemm_tcgen05_kernel<0><<<(unsigned)grid, kThreads, smem, st>>>(tmA, tmB, p);
+    else gemm_tcgen05_kernel<1><<<(unsigned)grid, kThreads, smem, st>>>(tmA, tmB, p);
+  } else {
+    const int64_t pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
+    if (kind == 0) gemm_tcgen05_2cta_kernel<0><<<(unsigned)(2 * pairs), kThreads, smem, st>>>(tmA, tmB, p);
+    else gemm_tcgen05_2cta_kernel<1><<<(unsigned)(2 * pairs), kThreads, smem, st>>>(tmA, tmB, p);
+  }
   TNB_LAUNCH_CHECK();
   count_launch();
-  set_kernel_name(g.dtype == TNB200_BF16 ? "tcgen05_bf16" : (g.dtype == TNB200_F16 ? "tcgen05_f16" : "tcgen05_tf32"));
+  if (use2) set_kernel_name(g.dtype == TNB200_BF16 ? "tcgen05_2cta_bf16" : (g.dtype == TNB200_F16 ? "tcgen05_2cta_f16" : "tcgen05_2cta_tf32"));
+  else set_kernel_name(g.dtype == TNB200_BF16 ? "tcgen05_bf16" : (g.dtype == TNB200_F16 ? "tcgen05_f16" : "tcgen05_tf32"));
   return 0;
 }
 

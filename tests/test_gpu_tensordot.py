@@ -52,7 +52,9 @@ def test_oracle_random(dtype, case):
                      b.astype("float32") if dtype == "float16" else b, axes)
   out = be.tensordot(be.convert_to_tensor(a), be.convert_to_tensor(b), axes)
   assert out.shape == ref.shape
-  assert_close(out, ref.astype(dtype) if dtype.startswith("int") else ref, dtype=dtype)
+  kern = be.lib.tnb200_last_kernel().decode()
+  tol = TOL["tf32"] if (dtype == "float32" and kern.startswith("tcgen05")) else None   # fp32 on tensor cores = TF32
+  assert_close(out, ref.astype(dtype) if dtype.startswith("int") else ref, dtype=dtype, tol=tol)
 
 
 def test_strided_views_and_permutes():

@@ -54,6 +54,32 @@ if __name__ == "__main__":
     run(be, dt, (64, 1024, 512), (64, 512, 1024), None, reps=3, batch=True)
     run(be, dt, (512, 2, 512), (512, 2, 512), [[2], [0]], reps=3)
     sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "--cfg2steps":
+    # the two bulk steps of the cfg-2 zipper, batched over NB samples, timed individually
+    dt = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+    tdt = {"bf16": torch.bfloat16, "f32": torch.float32, "f64": torch.float64}[dt]
+    for nb in (1, 8, 32):
+      A = tb.B200Tensor(torch.randn((nb, 512, 2, 512), device=be.device, dtype=torch.float32).to(tdt))
+      E = tb.B200Tensor(torch.randn((nb, 512, 512), device=be.device, dtype=torch.float32).to(tdt))
+      Tt = tb.B200Tensor(torch.randn((nb, 2, 512, 512), device=be.device, dtype=torch.float32).to(tdt))
+      for name, f, fl in (("a: A(512,2,512)[0] x E(512,512)[1]", lambda: be._contract(A, E, [1], [2], [0], [0]), 2.0 * 1024 * 512 * 512),
+                          ("b: A(512,2,512)[0,1] x T(2,512,512)[2,0]", lambda: be._contract(A, Tt, [1, 2], [3, 1], [0], [0]), 2.0 * 512 * 1024 * 512)):
+        for _ in range(3):
+          f()
+        torch.cuda.synchronize()
+        l0 = be.lib.tnb200_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+          for _ in range(20):
+            f()
+        nl = (be.lib.tnb200_launch_count() - l0) / 20
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        print(json.dumps({"step": name, "nb": nb, "dtype": dt, "kernel": be.lib.tnb200_last_kernel().decode(),
+                          "launches": nl, "us": us, "tflops": nb * fl / us / 1e6}))
+    sys.exit(0)
   for dt in ("bf16", "f32", "f64"):
     run(be, dt, (512, 2, 512), (512, 2, 512), [[2], [0]])
     run(be, dt, (512, 2, 512), (512, 2, 512), [[0], [2]])
