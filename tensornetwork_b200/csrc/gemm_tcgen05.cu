@@ -113,6 +113,102 @@ constexpr int kBM = 128;
 constexpr int kRowBytes = 128;        // one swizzle row = BK elements
 constexpr int kThreads = 256;
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  const uint32_t leader_bar = bar & 0xFEFFFFFFu;   // peer bit cleared: transaction bytes land on CTA 0's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void tc_mma_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (KIND == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// TMA producer, executed by ALL 32 lanes of warp 0: lane l owns "load slot" l of a stage — one
+// 128-byte-wide box of A (slots 0..nA-1) or of B (slots nA..nA+nB-1).  Per-tile work (tile decode,
+// free-mode coordinates of the slot) is done once per tile; inside the k loop a lane only advances
+// its contracted-mode coordinates incrementally (no division) and issues its own TMA, so the boxes
+// of a stage are issued in parallel instead of by one thread in sequence.
+template <int KIND, bool TWO>
+__device__ __forceinline__ void tma_producer(const CUtensorMap* tmA, const CUtensorMap* tmB, const TcParams& p, uint8_t* smem,
+                                             uint32_t bar_base, int S, int stage_bytes, int b_rows, uint32_t rank,
+                                             int64_t first, int64_t step, int lane) {
+  constexpr int ES = KIND == 0 ? 2 : 4;
+  constexpr int BK = kRowBytes / ES;
+  constexpr int CHUNK = kRowBytes / ES;
+  constexpr int A_BYTES = kBM * kRowBytes;
+  const int nA = p.a_mn ? kBM / CHUNK : 1;
+  const int nB = p.b_mn ? b_rows / CHUNK : 1;
+  const bool mine = lane < nA + nB;
+  const bool is_a = lane < nA;
+  const int c = is_a ? lane : lane - nA;                       // chunk index inside the operand tile
+  const bool mn = is_a ? (p.a_mn != 0) : (p.b_mn != 0);
+  const uint32_t fe = is_a ? p.a_fe : p.b_fe, ke = is_a ? p.a_ke : p.b_ke;
+  const CUtensorMap* map = is_a ? tmA : tmB;
+  const uint32_t dst_off = (is_a ? 0u : (uint32_t)A_BYTES) + (mn ? (uint32_t)c * (BK * kRowBytes) : 0u);
+  const uint32_t tiles_n = (uint32_t)p.tiles_n, tiles_m = (uint32_t)p.tiles_m;
+  int s = 0; uint32_t ph = 0;
+  for (int64_t tile64 = first; tile64 < p.num_tiles; tile64 += step) {
+    uint32_t t = (uint32_t)tile64;
+    const uint32_t ni = t % tiles_n; t /= tiles_n;
+    const uint32_t mi = t % tiles_m;
+    const int bi = (int)(t / tiles_m);
+    int f;   // first free-mode (row) index of this lane's box
+    if (is_a) f = (int)mi * (TWO ? 2 * kBM : kBM) + (TWO ? (int)rank * kBM : 0) + (mn ? c * CHUNK : 0);
+    else f = (int)ni * p.BN + (TWO ? (int)rank * b_rows : 0) + (mn ? c * CHUNK : 0);
+    const int f_in = fe ? (int)((uint32_t)f % fe) : f, f_out = fe ? (int)((uint32_t)f / fe) : 0;
+    int k_in = 0, k_out = 0;
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      mbar_wait(bar_base + 8u * (S + s), ph ^ 1);               // slot free (every lane observes it)
+      const uint32_t full = bar_base + 8u * s;
+      if (lane == 0) {
+        if (!TWO) mbar_expect_tx(full, (uint32_t)stage_bytes);
+        else if (rank == 0) mbar_expect_tx(full, (uint32_t)(2 * stage_bytes));
+        else mbar_arrive_remote(full, 0);
+      }
+      __syncwarp();
+      if (mine) {
+        const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes) + dst_off;
+        if (!mn) { if (TWO) tma_load_5d_2sm(dst, map, full, k_in, f_in, f_out, k_out, bi); else tma_load_5d(dst, map, full, k_in, f_in, f_out, k_out, bi); }
+        else     { if (TWO) tma_load_5d_2sm(dst, map, full, f_in, k_in, k_out, f_out, bi); else tma_load_5d(dst, map, full, f_in, k_in, k_out, f_out, bi); }
+      }
+      k_in += BK;
+      if (ke && (uint32_t)k_in >= ke) { k_in = 0; ++k_out; }
+      if (++s == S) { s = 0; ph ^= 1; }
+    }
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -159,48 +255,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int num_kb = p.num_kb;
   const int64_t first = blockIdx.x, step = gridDim.x;
 
-  if (warp == 0 && lane == 0) {
-    // ===================================================== TMA producer
-    int s = 0; uint32_t ph = 0;
-    for (int64_t tile = first; tile < p.num_tiles; tile += step) {
-      int64_t t = tile;
-      const int ni = (int)(t % p.tiles_n); t /= p.tiles_n;
-      const int mi = (int)(t % p.tiles_m);
-      const int bi = (int)(t / p.tiles_m);
-      const int m0 = mi * kBM, n0 = ni * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(s), ph ^ 1);
-        mbar_expect_tx(full_bar(s), (uint32_t)STAGE_BYTES);
-        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
-        const int k0 = kb * BK;
-        // split linear indices into (outer, inner) mode coordinates
-        const int ak_in = p.a_ke ? (int)(k0 % p.a_ke) : k0, ak_out = p.a_ke ? (int)(k0 / p.a_ke) : 0;
-        const int bk_in = p.b_ke ? (int)(k0 % p.b_ke) : k0, bk_out = p.b_ke ? (int)(k0 / p.b_ke) : 0;
-        if (!p.a_mn) {
-          const int f_in = p.a_fe ? (int)(m0 % p.a_fe) : m0, f_out = p.a_fe ? (int)(m0 / p.a_fe) : 0;
-          tma_load_5d(sa, &tmA, full_bar(s), ak_in, f_in, f_out, ak_out, bi);
-        } else {
-#pragma unroll
-          for (int c = 0; c < kBM / CHUNK; ++c) {
-            const int f = m0 + c * CHUNK;
-            const int f_in = p.a_fe ? (int)(f % p.a_fe) : f, f_out = p.a_fe ? (int)(f / p.a_fe) : 0;
-            tma_load_5d(sa + c * (BK * kRowBytes), &tmA, full_bar(s), f_in, ak_in, ak_out, f_out, bi);
-          }
-        }
-        if (!p.b_mn) {
-          const int f_in = p.b_fe ? (int)(n0 % p.b_fe) : n0, f_out = p.b_fe ? (int)(n0 / p.b_fe) : 0;
-          tma_load_5d(sb, &tmB, full_bar(s), bk_in, f_in, f_out, bk_out, bi);
-        } else {
-          for (int c = 0; c < BN / CHUNK; ++c) {
-            const int f = n0 + c * CHUNK;
-            const int f_in = p.b_fe ? (int)(f % p.b_fe) : f, f_out = p.b_fe ? (int)(f / p.b_fe) : 0;
-            tma_load_5d(sb + c * (BK * kRowBytes), &tmB, full_bar(s), f_in, bk_in, bk_out, f_out, bi);
-          }
-        }
-        if (++s == S) { s = 0; ph ^= 1; }
-      }
-    }
+  if (warp == 0) {
+    // ===================================================== TMA producer (whole warp, see tma_producer)
+    tma_producer<KIND, false>(&tmA, &tmB, p, smem, bar_base, S, STAGE_BYTES, BN, 0u, first, step, lane);
   } else if (warp == 1 && lane == 0) {
     // ===================================================== MMA issuer
     // descriptor fields per majorness (see DESIGN.md "UMMA operand layouts")
@@ -315,45 +372,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //   * TMA loads of both CTAs complete on the LEADER's full barrier (cta_group::2 + peer-bit mask);
 //   * tcgen05.commit multicasts the slot release / accumulator-ready signal to both CTAs;
 //   * both epilogues arrive (remotely for the peer) on the leader's tmem_empty barrier.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
-  uint32_t raddr;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(cta));
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  const uint32_t leader_bar = bar & 0xFEFFFFFFu;   // peer bit cleared: transaction bytes land on CTA 0's barrier
-  asm volatile(
-      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-template <int KIND>
-__device__ __forceinline__ void tc_mma_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  if (KIND == 0) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-  } else {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-  }
-}
-
 template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -404,48 +422,9 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_kb = p.num_kb;
   const int64_t first = blockIdx.x >> 1, step = gridDim.x >> 1;   // pair index
 
-  if (warp == 0 && lane == 0) {
-    // ===================================================== TMA producer (both CTAs)
-    int s = 0; uint32_t ph = 0;
-    for (int64_t tile = first; tile < p.num_tiles; tile += step) {
-      int64_t t = tile;
-      const int ni = (int)(t % p.tiles_n); t /= p.tiles_n;
-      const int mi = (int)(t % p.tiles_m);
-      const int bi = (int)(t / p.tiles_m);
-      const int m0 = mi * 2 * kBM + (int)rank * kBM, n0 = ni * BN + (int)rank * BNH;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(s), ph ^ 1);
-        if (leader) mbar_expect_tx(full_bar(s), (uint32_t)(2 * STAGE_BYTES));
-        else mbar_arrive_remote(full_bar(s), 0);
-        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
-        const int k0 = kb * BK;
-        const int ak_in = p.a_ke ? (int)(k0 % p.a_ke) : k0, ak_out = p.a_ke ? (int)(k0 / p.a_ke) : 0;
-        const int bk_in = p.b_ke ? (int)(k0 % p.b_ke) : k0, bk_out = p.b_ke ? (int)(k0 / p.b_ke) : 0;
-        if (!p.a_mn) {
-          const int f_in = p.a_fe ? (int)(m0 % p.a_fe) : m0, f_out = p.a_fe ? (int)(m0 / p.a_fe) : 0;
-          tma_load_5d_2sm(sa, &tmA, full_bar(s), ak_in, f_in, f_out, ak_out, bi);
-        } else {
-#pragma unroll
-          for (int c = 0; c < kBM / CHUNK; ++c) {
-            const int f = m0 + c * CHUNK;
-            const int f_in = p.a_fe ? (int)(f % p.a_fe) : f, f_out = p.a_fe ? (int)(f / p.a_fe) : 0;
-            tma_load_5d_2sm(sa + c * (BK * kRowBytes), &tmA, full_bar(s), f_in, ak_in, ak_out, f_out, bi);
-          }
-        }
-        if (!p.b_mn) {
-          const int f_in = p.b_fe ? (int)(n0 % p.b_fe) : n0, f_out = p.b_fe ? (int)(n0 / p.b_fe) : 0;
-          tma_load_5d_2sm(sb, &tmB, full_bar(s), bk_in, f_in, f_out, bk_out, bi);
-        } else {
-          for (int c = 0; c < BNH / CHUNK; ++c) {
-            const int f = n0 + c * CHUNK;
-            const int f_in = p.b_fe ? (int)(f % p.b_fe) : f, f_out = p.b_fe ? (int)(f / p.b_fe) : 0;
-            tma_load_5d_2sm(sb + c * (BK * kRowBytes), &tmB, full_bar(s), f_in, bk_in, bk_out, f_out, bi);
-          }
-        }
-        if (++s == S) { s = 0; ph ^= 1; }
-      }
-    }
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs, whole warp)
+    tma_producer<KIND, true>(&tmA, &tmB, p, smem, bar_base, S, STAGE_BYTES, BNH, rank, first, step, lane);
   } else if (warp == 1 && lane == 0 && leader) {
     // ===================================================== MMA issuer (leader CTA only)
     const uint32_t a_layout = (p.a_mn && KIND == 1) ? 1u : 2u;

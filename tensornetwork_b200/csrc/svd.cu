@@ -12,6 +12,7 @@
 // triplets are sorted in descending order by a rank-counting kernel.  R is orthogonal to working
 // precision, so the method is backward stable regardless of how accurately G was formed.
 #include "common.cuh"
+#include "cplx.cuh"
 #include <math.h>
 #include <vector>
 
@@ -41,35 +42,37 @@ __global__ void __launch_bounds__(256) svd_gram_kernel(const T* __restrict__ W, 
   const int64_t rows_per = ((R + rsplit - 1) / rsplit + RT - 1) / RT * RT;
   const int64_t r0 = chunk * rows_per, r1 = min(R, r0 + rows_per);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  T acc[2][2] = {{0, 0}, {0, 0}};
+  T acc[2][2];
+  acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = zero_<T>();
   for (int64_t rb = r0; rb < r1; rb += RT) {
     for (int idx = threadIdx.x; idx < PB * RT; idx += 256) {
       int c = idx / RT, rr = idx % RT;
       int64_t row = rb + rr;
-      tile[c][rr] = row < r1 ? W[(int64_t)pair_col(bi, bj, c) * R + row] : T(0);
+      tile[c][rr] = row < r1 ? W[(int64_t)pair_col(bi, bj, c) * R + row] : zero_<T>();
     }
     __syncthreads();
 #pragma unroll 8
     for (int rr = 0; rr < RT; ++rr) {
-      T a0 = tile[ty * 2][rr], a1 = tile[ty * 2 + 1][rr], b0 = tile[tx * 2][rr], b1 = tile[tx * 2 + 1][rr];
-      acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+      T a0 = cj(tile[ty * 2][rr]), a1 = cj(tile[ty * 2 + 1][rr]), b0 = tile[tx * 2][rr], b1 = tile[tx * 2 + 1][rr];
+      fmacc(acc[0][0], a0, b0); fmacc(acc[0][1], a0, b1); fmacc(acc[1][0], a1, b0); fmacc(acc[1][1], a1, b1);
     }
     __syncthreads();
   }
-  T* g = G + (int64_t)pair * PB * PB;
+  T* g = G + (int64_t)pair * PB * PB;     // G = W^H W (Hermitian)
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b) atomicAdd(&g[(ty * 2 + a) * PB + tx * 2 + b], acc[a][b]);
+    for (int b = 0; b < 2; ++b) atomic_add(&g[(ty * 2 + a) * PB + tx * 2 + b], acc[a][b]);
 }
 
 // Diagonalise the PB x PB Gram matrix of each pair; write the rotation, clear G for the next round,
 // record the largest relative off-diagonal seen BEFORE rotating (sweep convergence measure).
 template <typename T>
-__global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __restrict__ Rout, unsigned int* conv, T tol_inner) {
+__global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __restrict__ Rout, unsigned int* conv, double tol_inner) {
   __shared__ T g[PB][PB + 1];
   __shared__ T rm[PB][PB + 1];
-  __shared__ T cs[SB], sn[SB];
+  __shared__ double cs[SB], sn[SB];
+  __shared__ T ph[SB];          // e^{-i phi} of the pivot (real case: its sign is folded into t instead)
   __shared__ int pp[SB], qq[SB];
   __shared__ float red[8];
   __shared__ float offmax;
@@ -78,8 +81,8 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
   for (int idx = tid; idx < PB * PB; idx += 256) {
     int i = idx / PB, j = idx % PB;
     g[i][j] = gg[idx];
-    rm[i][j] = i == j ? T(1) : T(0);
-    gg[idx] = T(0);
+    rm[i][j] = i == j ? one_<T>() : zero_<T>();
+    gg[idx] = zero_<T>();
   }
   __syncthreads();
   for (int sweep = 0; sweep < 10; ++sweep) {
@@ -88,8 +91,8 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
     for (int idx = tid; idx < PB * PB; idx += 256) {
       int i = idx / PB, j = idx % PB;
       if (i < j) {
-        T d = g[i][i] * g[j][j];
-        if (d > T(0)) { float v = (float)(fabs((double)g[i][j]) / sqrt((double)d)); loc = fmaxf(loc, v); }
+        double d = re_(g[i][i]) * re_(g[j][j]);
+        if (d > 0.0) { float v = (float)(sqrt(ab2(g[i][j])) / sqrt(d)); loc = fmaxf(loc, v); }
       }
     }
     for (int o = 16; o > 0; o >>= 1) loc = fmaxf(loc, __shfl_xor_sync(0xffffffffu, loc, o));
@@ -109,34 +112,44 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
         int p, q;
         if (tid == 0) { p = m; q = step % m; } else { p = (step + tid) % m; q = (step - tid + m) % m; }
         if (p > q) { int t = p; p = q; q = t; }
-        T apq = g[p][q], app = g[p][p], aqq = g[q][q];
-        T c = T(1), s = T(0);
-        if (apq != T(0) && fabs((double)apq) > 1e-300) {
-          T tau = (aqq - app) / (T(2) * apq);
-          T t = (tau >= T(0) ? T(1) : T(-1)) / (fabs(tau) + sqrt(T(1) + tau * tau));
-          c = T(1) / sqrt(T(1) + t * t);
+        // Hermitian 2x2 [[a, g], [conj g, b]], g = |g| e^{i phi}: rotate (x_p, e^{-i phi} x_q) by the
+        // real Jacobi angle of [[a, |g|], [|g|, b]]
+        const T gpq = g[p][q];
+        const double app = re_(g[p][p]), aqq = re_(g[q][q]);
+        const double mag = sqrt(ab2(gpq));
+        double c = 1.0, s = 0.0;
+        T e = one_<T>();
+        if (mag > 1e-300) {
+          e = unit_conj_phase(gpq);
+          const double tau = (aqq - app) / (2.0 * mag);
+          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+          c = 1.0 / sqrt(1.0 + t * t);
           s = t * c;
         }
-        cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
+        cs[tid] = c; sn[tid] = s; ph[tid] = e; pp[tid] = p; qq[tid] = q;
       }
       __syncthreads();
       // column rotations of G and of the accumulated eigenvector matrix
+      // columns:  x_p' = c x_p - s e x_q ,  x_q' = s x_p + c e x_q      (e = e^{-i phi})
       for (int idx = tid; idx < SB * PB; idx += 256) {
         int k = idx / PB, i = idx % PB;
-        T c = cs[k], s = sn[k];
+        const double c = cs[k], s = sn[k];
+        const T e = ph[k];
         int p = pp[k], q = qq[k];
-        T x = g[i][p], y = g[i][q];
-        g[i][p] = c * x - s * y; g[i][q] = s * x + c * y;
-        x = rm[i][p]; y = rm[i][q];
-        rm[i][p] = c * x - s * y; rm[i][q] = s * x + c * y;
+        T x = g[i][p], y = mul(e, g[i][q]);
+        g[i][p] = sub(mulr(x, c), mulr(y, s)); g[i][q] = add(mulr(x, s), mulr(y, c));
+        x = rm[i][p]; y = mul(e, rm[i][q]);
+        rm[i][p] = sub(mulr(x, c), mulr(y, s)); rm[i][q] = add(mulr(x, s), mulr(y, c));
       }
       __syncthreads();
+      // rows (J^H G):  r_p' = c r_p - s conj(e) r_q ,  r_q' = s r_p + c conj(e) r_q
       for (int idx = tid; idx < SB * PB; idx += 256) {
         int k = idx / PB, j = idx % PB;
-        T c = cs[k], s = sn[k];
+        const double c = cs[k], s = sn[k];
+        const T e = cj(ph[k]);
         int p = pp[k], q = qq[k];
-        T x = g[p][j], y = g[q][j];
-        g[p][j] = c * x - s * y; g[q][j] = s * x + c * y;
+        T x = g[p][j], y = mul(e, g[q][j]);
+        g[p][j] = sub(mulr(x, c), mulr(y, s)); g[q][j] = add(mulr(x, s), mulr(y, c));
       }
       __syncthreads();
     }
@@ -148,8 +161,8 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
 // X[:, pair columns] <- X[:, pair columns] * R   (X = W or V; column-contiguous with `rows` rows)
 template <typename T>
 __global__ void __launch_bounds__(256) svd_update_kernel(T* __restrict__ X, int64_t rows, int nb, int round, const T* __restrict__ Rm) {
-  __shared__ T tile[PB][RT + 1];
-  __shared__ T rs[PB][PB + 1];
+  __shared__ T tile[PB][RT];     // read as tile[k][row]: consecutive threads -> consecutive rows (no padding needed)
+  __shared__ T rs[PB][PB];       // read as broadcast
   const int pair = blockIdx.x;
   int bi, bj;
   rr_pair(nb, round, pair, bi, bj);
@@ -161,17 +174,17 @@ __global__ void __launch_bounds__(256) svd_update_kernel(T* __restrict__ X, int6
     for (int idx = threadIdx.x; idx < PB * RT; idx += 256) {
       int c = idx / RT, r2 = idx % RT;
       int64_t row = rb + r2;
-      tile[c][r2] = row < rows ? X[(int64_t)pair_col(bi, bj, c) * rows + row] : T(0);
+      tile[c][r2] = row < rows ? X[(int64_t)pair_col(bi, bj, c) * rows + row] : zero_<T>();
     }
     __syncthreads();
     T out[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) out[c] = T(0);
+    for (int c = 0; c < 8; ++c) out[c] = zero_<T>();
 #pragma unroll 8
     for (int k = 0; k < PB; ++k) {
       T x = tile[k][rr];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) out[c] += x * rs[k][cg * 8 + c];
+      for (int c = 0; c < 8; ++c) fmacc(out[c], x, rs[k][cg * 8 + c]);
     }
     int64_t row = rb + rr;
     if (row < rows) {
@@ -182,11 +195,11 @@ __global__ void __launch_bounds__(256) svd_update_kernel(T* __restrict__ X, int6
 }
 
 template <typename T>
-__global__ void svd_colnorm_kernel(const T* __restrict__ W, int64_t R, int ncols, T* __restrict__ sig) {
+__global__ void svd_colnorm_kernel(const T* __restrict__ W, int64_t R, int ncols, double* __restrict__ sig) {
   const int j = blockIdx.x;
   if (j >= ncols) return;
   double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) { double v = (double)W[(int64_t)j * R + i]; acc += v * v; }
+  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) acc += ab2(W[(int64_t)j * R + i]);
   __shared__ double red[32];
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -194,45 +207,45 @@ __global__ void svd_colnorm_kernel(const T* __restrict__ W, int64_t R, int ncols
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
-    sig[j] = (T)sqrt(t);
+    sig[j] = sqrt(t);
   }
 }
 // descending rank by counting (stable: ties keep column order)
-template <typename T>
-__global__ void svd_rank_kernel(const T* __restrict__ sig, int n, int* __restrict__ rank) {
+__global__ void svd_rank_kernel(const double* __restrict__ sig, int n, int* __restrict__ rank) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  T sj = sig[j];
+  double sj = sig[j];
   int r = 0;
-  for (int i = 0; i < n; ++i) { T si = sig[i]; r += (si > sj) || (si == sj && i < j); }
+  for (int i = 0; i < n; ++i) { double si = sig[i]; r += (si > sj) || (si == sj && i < j); }
   rank[j] = r;
 }
 // scatter the sorted triplets into the caller's u (m x r), s (r), vh (r x n); `tall` = input had m >= n
 template <typename T>
-__global__ void svd_finalize_kernel(const T* __restrict__ W, const T* __restrict__ V, const T* __restrict__ sig,
+__global__ void svd_finalize_kernel(const T* __restrict__ W, const T* __restrict__ V, const double* __restrict__ sig,
                                     const int* __restrict__ rank, int64_t R, int Cn, int Cp, int r_out, int tall,
-                                    T* __restrict__ u, int64_t u_s0, int64_t u_s1, T* __restrict__ s, int64_t s_s0,
+                                    T* __restrict__ u, int64_t u_s0, int64_t u_s1, double* __restrict__ s, int64_t s_s0,
                                     T* __restrict__ vh, int64_t v_s0, int64_t v_s1) {
   const int j = blockIdx.x;          // working column
   const int k = rank[j];
   if (k >= r_out) return;
-  const T sg = sig[j];
-  const T inv = sg > T(0) ? T(1) / sg : T(0);
+  const double sg = sig[j];
+  const double inv = sg > 0.0 ? 1.0 / sg : 0.0;
   if (threadIdx.x == 0) s[(int64_t)k * s_s0] = sg;
-  // left factor of the WORK matrix: W[:, j] / sigma (length R); right factor: V[:, j] (length Cn)
+  // WORK = A (tall) or A^H (wide) = Wn S V^H with Wn = W / sigma.
+  //   tall: u = Wn, vh = V^H            wide: A = V S Wn^H  ->  u = V, vh = Wn^H
   for (int64_t i = threadIdx.x; i < R; i += blockDim.x) {
-    T val = W[(int64_t)j * R + i] * inv;
-    if (tall) u[i * u_s0 + (int64_t)k * u_s1] = val; else vh[(int64_t)k * v_s0 + i * v_s1] = val;
+    T val = mulr(W[(int64_t)j * R + i], inv);
+    if (tall) u[i * u_s0 + (int64_t)k * u_s1] = val; else vh[(int64_t)k * v_s0 + i * v_s1] = cj(val);
   }
   for (int64_t i = threadIdx.x; i < Cn; i += blockDim.x) {
     T val = V[(int64_t)j * Cp + i];
-    if (tall) vh[(int64_t)k * v_s0 + i * v_s1] = val; else u[i * u_s0 + (int64_t)k * u_s1] = val;
+    if (tall) vh[(int64_t)k * v_s0 + i * v_s1] = cj(val); else u[i * u_s0 + (int64_t)k * u_s1] = val;
   }
 }
 template <typename T>
 __global__ void svd_eye_kernel(T* V, int Cp) {
   int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (idx < (int64_t)Cp * Cp) V[idx] = (idx / Cp == idx % Cp) ? T(1) : T(0);
+  if (idx < (int64_t)Cp * Cp) V[idx] = (idx / Cp == idx % Cp) ? one_<T>() : zero_<T>();
 }
 
 template <typename T>
@@ -245,7 +258,8 @@ static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tn
   const int Cp = (Cn + PB - 1) / PB * PB;
   const int nb = Cp / SB, npairs = nb / 2, rounds = nb - 1;
   if (Cn == 0 || R == 0) return 0;
-  T *W = nullptr, *V = nullptr, *G = nullptr, *Rm = nullptr, *sig = nullptr;
+  T *W = nullptr, *V = nullptr, *G = nullptr, *Rm = nullptr;
+  double* sig = nullptr;
   int* rank = nullptr;
   unsigned int* conv = nullptr;
   int rc;
@@ -253,7 +267,7 @@ static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tn
   if ((rc = ws_alloc((void**)&V, sizeof(T) * (size_t)Cp * Cp, st))) return rc;
   if ((rc = ws_alloc((void**)&G, sizeof(T) * (size_t)npairs * PB * PB, st))) return rc;
   if ((rc = ws_alloc((void**)&Rm, sizeof(T) * (size_t)npairs * PB * PB, st))) return rc;
-  if ((rc = ws_alloc((void**)&sig, sizeof(T) * (size_t)Cp, st))) return rc;
+  if ((rc = ws_alloc((void**)&sig, sizeof(double) * (size_t)Cp, st))) return rc;
   if ((rc = ws_alloc((void**)&rank, sizeof(int) * (size_t)Cp, st))) return rc;
   if ((rc = ws_alloc((void**)&conv, sizeof(unsigned int) * 64, st))) return rc;
   TNB_CHECK_CUDA(cudaMemsetAsync(W, 0, sizeof(T) * (size_t)Cp * R, st));
@@ -263,13 +277,13 @@ static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tn
   if (!tall) { src.shape[0] = a->shape[1]; src.shape[1] = a->shape[0]; src.stride[0] = a->stride[1]; src.stride[1] = a->stride[0]; }
   dst.data = W; dst.dtype = a->dtype; dst.ndim = 2;
   dst.shape[0] = R; dst.shape[1] = Cn; dst.stride[0] = 1; dst.stride[1] = R;
-  if ((rc = copy_strided(&src, &dst, 0, st))) return rc;
+  if ((rc = copy_strided(&src, &dst, tall ? 0 : 1, st))) return rc;   // wide: WORK = A^H (conjugated)
   svd_eye_kernel<T><<<(unsigned)(((int64_t)Cp * Cp + 255) / 256), 256, 0, st>>>(V, Cp);
   count_launch();
 
-  const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920929e-07;
+  const double eps = 2.220446049250313e-16;
   const double tol = 4.0 * sqrt((double)R) * eps;
-  const T tol_inner = (T)(sizeof(T) == 8 ? 1e-15 : 1e-7);
+  const double tol_inner = 1e-15;
   int rsplit = (4 * num_sms() + npairs - 1) / npairs;
   int max_split = (int)((R + 4 * RT - 1) / (4 * RT));
   if (rsplit > max_split) rsplit = max_split;
@@ -297,9 +311,9 @@ static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tn
     if ((double)off <= tol) { converged = 1; break; }
   }
   svd_colnorm_kernel<T><<<Cp, 256, 0, st>>>(W, R, Cp, sig);
-  svd_rank_kernel<T><<<(Cp + 255) / 256, 256, 0, st>>>(sig, Cp, rank);
+  svd_rank_kernel<<<(Cp + 255) / 256, 256, 0, st>>>(sig, Cp, rank);
   svd_finalize_kernel<T><<<Cp, 256, 0, st>>>(W, V, sig, rank, R, Cn, Cp, Cn, tall ? 1 : 0, (T*)u->data, u->stride[0], u->stride[1],
-                                             (T*)s->data, s->stride[0], (T*)vh->data, vh->stride[0], vh->stride[1]);
+                                             (double*)s->data, s->stride[0], (T*)vh->data, vh->stride[0], vh->stride[1]);
   count_launch(3);
   TNB_LAUNCH_CHECK();
   if (info_dev) {
@@ -348,30 +362,35 @@ extern "C" int32_t tnb200_svd(const tnb200_tensor_t* a, const tnb200_tensor_t* u
   cudaStream_t st = (cudaStream_t)stream;
   set_kernel_name("svd_block_jacobi");
   if (a->dtype == TNB200_F64) { TNB_REQUIRE(s->dtype == TNB200_F64, TNB200_ERR_DTYPE, "svd: s must be f64"); return svd_real<double>(a, u, s, vh, info_dev, st); }
-  if (a->dtype == TNB200_F32) {
-    // float32 input: iterate in double (hundreds of accumulated plane rotations cost ~1e-5 relative
-    // accuracy in fp32, LAPACK's sgesdd delivers ~1e-6), then round the factors back to float32.
+  if (a->dtype == TNB200_C128) { TNB_REQUIRE(s->dtype == TNB200_F64, TNB200_ERR_DTYPE, "svd: s must be f64"); return svd_real<zd>(a, u, s, vh, info_dev, st); }
+  if (a->dtype == TNB200_F32 || a->dtype == TNB200_C64) {
+    // single precision input: iterate in double (hundreds of accumulated plane rotations cost ~1e-5
+    // relative accuracy in fp32, LAPACK's sgesdd delivers ~1e-6), then round the factors back.
+    const bool cplx = a->dtype == TNB200_C64;
     TNB_REQUIRE(s->dtype == TNB200_F32, TNB200_ERR_DTYPE, "svd: s must be f32");
-    double *da = nullptr, *du = nullptr, *ds = nullptr, *dv = nullptr;
+    const int wide_dt = cplx ? TNB200_C128 : TNB200_F64;
+    const size_t esz = cplx ? 16 : 8;
+    void *da = nullptr, *du = nullptr, *dv = nullptr;
+    double* ds = nullptr;
     int rc;
-    if ((rc = ws_alloc((void**)&da, sizeof(double) * (size_t)m * n, st))) return rc;
-    if ((rc = ws_alloc((void**)&du, sizeof(double) * (size_t)m * r, st))) return rc;
+    if ((rc = ws_alloc(&da, esz * (size_t)m * n, st))) return rc;
+    if ((rc = ws_alloc(&du, esz * (size_t)m * r, st))) return rc;
     if ((rc = ws_alloc((void**)&ds, sizeof(double) * (size_t)r, st))) return rc;
-    if ((rc = ws_alloc((void**)&dv, sizeof(double) * (size_t)r * n, st))) return rc;
-    auto mk = [](void* p, int64_t d0, int64_t d1, int nd) {
-      tnb200_tensor_t t; t.data = p; t.dtype = TNB200_F64; t.ndim = nd;
+    if ((rc = ws_alloc(&dv, esz * (size_t)r * n, st))) return rc;
+    auto mk = [](void* p, int dt, int64_t d0, int64_t d1, int nd) {
+      tnb200_tensor_t t; t.data = p; t.dtype = dt; t.ndim = nd;
       t.shape[0] = d0; t.shape[1] = d1; t.stride[0] = nd == 2 ? d1 : 1; t.stride[1] = 1; return t;
     };
-    tnb200_tensor_t ta = mk(da, m, n, 2), tu = mk(du, m, r, 2), ts = mk(ds, r, 1, 1), tv = mk(dv, r, n, 2);
+    tnb200_tensor_t ta = mk(da, wide_dt, m, n, 2), tu = mk(du, wide_dt, m, r, 2), ts = mk(ds, TNB200_F64, r, 1, 1), tv = mk(dv, wide_dt, r, n, 2);
     if ((rc = copy_strided(a, &ta, 0, st))) return rc;
-    rc = svd_real<double>(&ta, &tu, &ts, &tv, info_dev, st);
+    rc = cplx ? svd_real<zd>(&ta, &tu, &ts, &tv, info_dev, st) : svd_real<double>(&ta, &tu, &ts, &tv, info_dev, st);
     if (rc == 0) rc = copy_strided(&tu, u, 0, st);
     if (rc == 0) rc = copy_strided(&ts, s, 0, st);
     if (rc == 0) rc = copy_strided(&tv, vh, 0, st);
     ws_free(da, st); ws_free(du, st); ws_free(ds, st); ws_free(dv, st);
     return rc;
   }
-  set_error("svd: dtype %s is not supported yet (f32/f64 only)", dtype_name(a->dtype));
+  set_error("svd: dtype %s is not supported (f32/f64/c64/c128)", dtype_name(a->dtype));
   return TNB200_ERR_UNSUPPORTED;
 }
 

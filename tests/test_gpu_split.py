@@ -42,8 +42,6 @@ def test_golden_decompositions():
   meta, z = load_golden("decomp")
   for i, m in enumerate(meta):
     x = z["in%d" % i]
-    if np.iscomplexobj(x):
-      continue  # complex split: see test_complex_split_not_yet / DESIGN.md
     if m["kind"] == "svd":
       _check_svd(be, x, m["kwargs"])
       got = be.svd(be.convert_to_tensor(x), **m["kwargs"])
@@ -98,6 +96,31 @@ def test_svd_random_vs_oracle(shape, pivot, kw, dtype):
   rng = np.random.default_rng(31)
   x = rng.standard_normal(shape).astype(dtype)
   _check_svd(be, x, dict(pivot_axis=pivot, **kw))
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("shape,pivot,kw", [((24, 24), 1, {}), ((40, 17), 1, {"max_singular_values": 9}),
+                                            ((17, 40), 1, {}), ((4, 5, 6, 3), 2, {"max_truncation_error": 0.3, "relative": True})])
+def test_complex_svd_qr(dtype, shape, pivot, kw):
+  """split_node_test.py:63-73 exercises complex64 SVD; s is returned in the (complex) input dtype."""
+  be = get_backend()
+  rng = np.random.default_rng(34)
+  x = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(dtype)
+  _check_svd(be, x, dict(pivot_axis=pivot, **kw))
+  u, s, vh, rest = be.svd(be.convert_to_tensor(x), pivot_axis=pivot, **kw)
+  assert s.dtype == np.dtype(dtype)
+  tol = 1e-10 if dtype == "complex128" else 2e-5
+  for nn in (False, True):
+    q, r = be.qr(be.convert_to_tensor(x), pivot, nn)
+    rq_, rr_ = nb.qr(x, pivot, nn)
+    k = rq_.shape[-1]
+    qh, rh = q.to_host(), r.to_host()
+    assert qh.shape == rq_.shape and rh.shape == rr_.shape
+    np.testing.assert_allclose(qh, rq_, atol=200 * tol * max(1.0, np.abs(rq_).max()))
+    np.testing.assert_allclose(rh, rr_, atol=200 * tol * max(1.0, np.abs(rr_).max()))
+    r2, q2 = be.rq(be.convert_to_tensor(x), pivot, nn)
+    m2 = r2.to_host().reshape(-1, r2.shape[-1]) @ q2.to_host().reshape(q2.shape[0], -1)
+    assert rel_err(m2, x.reshape(m2.shape)) < 50 * tol
 
 
 def test_svd_rank_deficient_and_graded():
