@@ -298,6 +298,36 @@ def gen_blocksparse(tn):
   _save("blocksparse", meta, arrays)
 
 
+def gen_dmrg(tn):
+  """FiniteDMRG.run_two_site (matrixproductstates/dmrg.py:445) on XXZ chains: initial MPS tensors, the
+  reference's final energy, and the exact-diagonalisation energy (dmrg_test.py:161-191 style)."""
+  meta, arrays = [], {}
+  for ci, (N, D, sweeps) in enumerate([(6, 8, 4), (8, 16, 4), (10, 12, 3)]):
+    np.random.seed(10 + ci)
+    mps = tn.FiniteMPS.random([2] * N, [D] * (N - 1), dtype=np.float64, backend="numpy")
+    for j, t in enumerate(mps.tensors):
+      arrays["c%d_mps%d" % (ci, j)] = np.array(t)
+    mpo = tn.FiniteXXZ(np.ones(N - 1), np.ones(N - 1), np.zeros(N), dtype=np.float64, backend="numpy")
+    for j, t in enumerate(mpo.tensors):
+      arrays["c%d_mpo%d" % (ci, j)] = np.array(t)
+    center = mps.center_position
+    dm = tn.FiniteDMRG(mps, mpo)
+    e = float(dm.run_two_site(max_bond_dim=D, num_sweeps=sweeps, num_krylov_vecs=10, verbose=2))
+    # exact diagonalisation of the same Hamiltonian
+    sz = np.diag([-0.5, 0.5]); sp = np.array([[0, 0], [1.0, 0]]); sm = sp.T
+    H = np.zeros((2**N, 2**N))
+    def op(o, i):
+      m = np.eye(1)
+      for k in range(N):
+        m = np.kron(m, o if k == i else np.eye(2))
+      return m
+    for i in range(N - 1):
+      H += op(sz, i) @ op(sz, i + 1) + 0.5 * (op(sp, i) @ op(sm, i + 1) + op(sm, i) @ op(sp, i + 1))
+    ed = float(np.linalg.eigvalsh(H)[0])
+    meta.append(dict(N=N, D=D, sweeps=sweeps, center=int(center), energy=e, ed=ed))
+  _save("dmrg", meta, arrays)
+
+
 def main():
   tn = ref_shim.load()
   assert tn.__version__ == "0.4.6"
@@ -308,6 +338,7 @@ def main():
   gen_split(tn)
   gen_lanczos(tn)
   gen_blocksparse(tn)
+  gen_dmrg(tn)
 
 
 if __name__ == "__main__":

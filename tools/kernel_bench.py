@@ -54,6 +54,26 @@ if __name__ == "__main__":
     run(be, dt, (64, 1024, 512), (64, 512, 1024), None, reps=3, batch=True)
     run(be, dt, (512, 2, 512), (512, 2, 512), [[2], [0]], reps=3)
     sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "--svd":
+    import time
+    sizes = [int(x) for x in sys.argv[2:]] or [1024, 2048]
+    for n in sizes:
+      rng = np.random.default_rng(4)
+      m = rng.standard_normal((n, n)) / np.sqrt(n)
+      M = be.convert_to_tensor(m)
+      info = torch.zeros(4, dtype=torch.int32, device=be.device)
+      u = be._new((n, n), M.code); sv = be._new((n,), M.code); vh = be._new((n, n), M.code)
+      from tensornetwork_b200 import _lib as L
+      for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        L.check(be.lib.tnb200_svd(M.ref(), u.ref(), sv.ref(), vh.ref(), info.data_ptr(), be._stream()))
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+      t0 = time.perf_counter(); ref = np.linalg.svd(m, compute_uv=True, full_matrices=False); tc = time.perf_counter() - t0
+      err = float(np.abs(sv.to_host() - ref[1]).max() / ref[1][0])
+      rec = float(np.linalg.norm((u.to_host() * sv.to_host()) @ vh.to_host() - m) / np.linalg.norm(m))
+      print(json.dumps({"svd_n": n, "gpu_s": dt, "cpu_numpy_s": tc, "sweeps": int(info[0]), "converged": int(info[1]),
+                        "s_err_rel": err, "recon_rel": rec, "gflops_21n3": 21.0 * n**3 / dt / 1e9}))
+    sys.exit(0)
   if len(sys.argv) > 1 and sys.argv[1] == "--cfg2steps":
     # the two bulk steps of the cfg-2 zipper, batched over NB samples, timed individually
     dt = sys.argv[2] if len(sys.argv) > 2 else "bf16"
