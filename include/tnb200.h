@@ -176,6 +176,22 @@ TNB200_API int32_t tnb200_blocksparse_tensordot(const void* a_data, const void* 
                                      const int64_t* c_map_dev, const int64_t* c_off_dev,
                                      int64_t max_m, int64_t max_n, int32_t conj_b, void* stream);
 
+/* ---- a12: the per-sector SVDs of backends/symmetric/decompositions.py:54-61 (a Python loop of
+ * np.linalg.svd there): `nprob` independent small SVDs in ONE launch, one CTA per matrix, warp-shuffle
+ * Jacobi in shared memory.  Problem q: A_q is m_q x n_q, row-major contiguous at a_data + a_off[q]
+ * (element offsets); outputs U_q (m x r), S_q (r, real dtype, descending), Vh_q (r x n), r = min(m, n),
+ * row-major at the given offsets.  dims holds (m_q, n_q) pairs.  All arrays are device pointers.
+ * *status_dev (may be NULL) is set to 1 if any problem failed to converge. */
+TNB200_API int32_t tnb200_svd_batched(const void* a_data, int32_t dtype, int32_t nprob, const int64_t* dims_dev,
+                                      const int64_t* a_off_dev, void* u_data, const int64_t* u_off_dev, void* s_data,
+                                      const int64_t* s_off_dev, void* vh_data, const int64_t* vh_off_dev,
+                                      int64_t max_m, int64_t max_n, int32_t* status_dev, void* stream);
+
+/* dst[i] = src[idx[i]] (gather) or dst[idx[i]] = src[i] (scatter = 1), i < n; idx is a device int64 array.
+ * The fancy-index gathers of block_sparse (blocksparsetensor.py:1094-1101, symmetric decompositions.py:55). */
+TNB200_API int32_t tnb200_gather(const void* src, const int64_t* idx_dev, void* dst, int64_t n, int32_t dtype,
+                                 int32_t scatter, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

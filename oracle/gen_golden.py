@@ -298,6 +298,36 @@ def gen_blocksparse(tn):
   _save("blocksparse", meta, arrays)
 
 
+def gen_symsvd(tn):
+  """SymmetricBackend.svd (backends/symmetric/decompositions.py:27-216): singular values (kept, sector-major),
+  discarded values and the dense reconstruction, for several truncation settings."""
+  from tensornetwork.block_sparse import BlockSparseTensor, Index, U1Charge
+  be = tn.backends.backend_factory.get_backend("symmetric")
+  meta, arrays = [], {}
+  cases = [(11, 10, 2, [False, False, True, True], 2, {}),
+           (12, 10, 2, [False, False, True, True], 2, {"max_singular_values": 12}),
+           (13, 12, 3, [False, True, False, True], 2, {"max_truncation_error": 0.5}),
+           (14, 12, 2, [False, False, True], 1, {"max_truncation_error": 0.05, "relative": True, "max_singular_values": 9}),
+           (15, 8, 2, [True, False, True, False], 3, {"max_singular_values": 5})]
+  for ci, (seed, dim, q, flows, pivot, kw) in enumerate(cases):
+    np.random.seed(seed)
+    legs = [Index(U1Charge.random(dim, -q, q), f) for f in flows]
+    A = BlockSparseTensor.random(legs, dtype=np.float64)
+    U, S, V, Sd = be.svd(A, pivot, **kw)
+    for li, leg in enumerate(legs):
+      arrays["c%d_q%d" % (ci, li)] = np.asarray(leg.flat_charges[0].charges).ravel().astype(np.int64)
+    arrays["c%d_A" % ci] = np.asarray(A.data)
+    arrays["c%d_S" % ci] = np.asarray(S.data)
+    arrays["c%d_Sdisc" % ci] = np.asarray(Sd.data)
+    ud, vd = U.todense(), V.todense()
+    k = ud.shape[-1]
+    rec = np.tensordot(ud * np.asarray(S.todense()), vd, 1) if k else np.zeros(A.shape)
+    arrays["c%d_rec" % ci] = rec
+    arrays["c%d_dense" % ci] = A.todense()
+    meta.append(dict(flows=flows, pivot=pivot, kwargs=kw, nlegs=len(legs), k=int(k)))
+  _save("symsvd", meta, arrays)
+
+
 def gen_dmrg(tn):
   """FiniteDMRG.run_two_site (matrixproductstates/dmrg.py:445) on XXZ chains: initial MPS tensors, the
   reference's final energy, and the exact-diagonalisation energy (dmrg_test.py:161-191 style)."""
@@ -339,6 +369,7 @@ def main():
   gen_lanczos(tn)
   gen_blocksparse(tn)
   gen_dmrg(tn)
+  gen_symsvd(tn)
 
 
 if __name__ == "__main__":

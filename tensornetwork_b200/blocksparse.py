@@ -294,3 +294,128 @@ def tensordot(a, b, axes):
   out = BlockSparseTensor(c_data, out_indices, backend=be)
   out.last_flops = dev["flops"]
   return out
+
+
+# ===================================================================================== svd
+def _truncate_sectors(singvals, max_singular_values=None, max_truncation_error=None, relative=False):
+  """The cross-sector truncation of backends/symmetric/decompositions.py:63-136, restated on host
+  (integer outputs: how many singular values each sector keeps).  `singvals` = list of descending
+  per-sector arrays.  Returns (kept counts, list of discarded-value arrays)."""
+  orig = [len(s) for s in singvals]
+  total = int(np.sum(orig)) if orig else 0
+  if max_singular_values is not None and max_singular_values >= total:
+    max_singular_values = None
+  if max_truncation_error is None and max_singular_values is None:
+    return orig, [np.zeros(0, dtype=s.dtype) for s in singvals]
+  max_d = max(orig) if orig else 0
+  ext = np.stack([np.append(s, np.zeros(max_d - len(s), dtype=s.dtype)) for s in singvals], axis=1) \
+      if singvals else np.empty((0, 0))
+  flat = np.ravel(ext)
+  inds = np.argsort(flat, kind="stable")
+  disc = np.zeros(0, dtype=np.int64)
+  if max_truncation_error is not None:
+    if relative and singvals:
+      max_truncation_error = max_truncation_error * np.max([s[0] for s in singvals])
+    kept_mask = np.sqrt(np.cumsum(np.square(flat[inds]))) > max_truncation_error
+    disc = inds[np.logical_not(kept_mask)]
+    inds = inds[kept_mask]
+  if max_singular_values is not None:
+    if max_singular_values > total:
+      max_singular_values = total
+    if max_singular_values < len(inds):
+      disc = np.append(disc, inds[:(-1) * max_singular_values])
+      inds = inds[(-1) * max_singular_values:]
+  ncol = ext.shape[1]
+  keep = np.divmod(inds, ncol) if ncol else (np.zeros(0, dtype=np.int64),) * 2
+  dsc = np.divmod(disc, ncol) if ncol else (np.zeros(0, dtype=np.int64),) * 2
+  kept = [int(np.sum(keep[1] == n)) for n in range(ncol)]
+  discarded = []
+  for n in range(ncol):
+    d = ext[dsc[0][dsc[1] == n], dsc[1][dsc[1] == n]][::-1]
+    discarded.append(d[:orig[n] - kept[n]])
+  return kept, discarded
+
+
+def svd(tensor, pivot_axis, max_singular_values=None, max_truncation_error=None, relative=False):
+  """Block-sparse SVD (backends/symmetric/decompositions.py:27-216): one small SVD per charge sector —
+  all sectors in ONE `tnb200_svd_batched` launch — then the reference's global truncation.
+
+  Returns (U, S, V, Sdisc): U legs = left legs + [bond], V legs = [bond] + right legs (block-sparse);
+  S = dict(values=1-D device tensor of kept singular values, sector-major, index=bond Index);
+  Sdisc = host array of the discarded singular values (sector-major)."""
+  be = tensor.backend
+  torch = be.torch
+  nl = pivot_axis if pivot_axis >= 0 else tensor.ndim + pivot_axis
+  qn, dims, maps = _sector_maps(tensor.indices, tensor.order, nl)
+  code = tensor.data.code
+  if code not in (L.F64, L.F32, L.C64, L.C128):
+    raise TypeError("block-sparse svd needs a float32/float64/complex tensor")
+  nsect = len(maps)
+  ms, ns = dims[:, 0], dims[:, 1]
+  rs = np.minimum(ms, ns)
+  a_off = np.zeros(nsect + 1, dtype=np.int64); a_off[1:] = np.cumsum(ms * ns)
+  u_off = np.zeros(nsect + 1, dtype=np.int64); u_off[1:] = np.cumsum(ms * rs)
+  s_off = np.zeros(nsect + 1, dtype=np.int64); s_off[1:] = np.cumsum(rs)
+  v_off = np.zeros(nsect + 1, dtype=np.int64); v_off[1:] = np.cumsum(rs * ns)
+  up = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(be.device)
+  st = be._stream()  # pylint: disable=protected-access
+  a_buf = be._new((int(a_off[-1]),), code)  # pylint: disable=protected-access
+  gmap = up(np.concatenate(maps) if maps else np.zeros(0, dtype=np.int64))
+  L.check(be.lib.tnb200_gather(tensor.data.t.data_ptr(), gmap.data_ptr(), a_buf.t.data_ptr(), int(a_off[-1]), code, 0, st))
+  u_buf = be._new((int(u_off[-1]),), code)  # pylint: disable=protected-access
+  s_buf = be._new((int(s_off[-1]),), T.real_code(code))  # pylint: disable=protected-access
+  v_buf = be._new((int(v_off[-1]),), code)  # pylint: disable=protected-access
+  d_dims, d_ao, d_uo, d_so, d_vo = up(dims.reshape(-1)), up(a_off), up(u_off), up(s_off), up(v_off)
+  status = torch.zeros(1, dtype=torch.int32, device=be.device)
+  rc = be.lib.tnb200_svd_batched(a_buf.t.data_ptr(), code, nsect, d_dims.data_ptr(), d_ao.data_ptr(), u_buf.t.data_ptr(),
+                                 d_uo.data_ptr(), s_buf.t.data_ptr(), d_so.data_ptr(), v_buf.t.data_ptr(), d_vo.data_ptr(),
+                                 int(ms.max()) if nsect else 0, int(ns.max()) if nsect else 0, status.data_ptr(), st)
+  if rc == L.ERR_UNSUPPORTED:
+    # a sector too large for the shared-memory kernel: one blocked-Jacobi SVD per sector
+    for q in range(nsect):
+      m_, n_, r_ = int(ms[q]), int(ns[q]), int(rs[q])
+      a_q = B200Tensor(a_buf.t[a_off[q]:a_off[q + 1]].view(m_, n_), code)
+      u_q = B200Tensor(u_buf.t[u_off[q]:u_off[q + 1]].view(m_, r_), code)
+      s_q = B200Tensor(s_buf.t[s_off[q]:s_off[q + 1]], T.real_code(code))
+      v_q = B200Tensor(v_buf.t[v_off[q]:v_off[q + 1]].view(r_, n_), code)
+      L.check(be.lib.tnb200_svd(a_q.ref(), u_q.ref(), s_q.ref(), v_q.ref(), None, st))
+  else:
+    L.check(rc)
+  s_host = s_buf.to_host()            # the one D2H of this path: data-dependent output sizes
+  if int(status.item()) != 0:
+    raise RuntimeError("block-sparse svd: a sector failed to converge")
+  singvals = [s_host[s_off[q]:s_off[q + 1]] for q in range(nsect)]
+  kept, discarded = _truncate_sectors(singvals, max_singular_values, max_truncation_error, relative)
+  # gather maps from the packed factor buffers into the block-sparse data layouts of U, S, V
+  u_idx, s_idx, v_idx, bond_q = [], [], [], []
+  for q in range(nsect):
+    k, m_, n_, r_ = kept[q], int(ms[q]), int(ns[q]), int(rs[q])
+    if k == 0:
+      continue
+    b = np.arange(k)
+    u_idx.append((u_off[q] + np.arange(m_)[None, :] * r_ + b[:, None]).ravel())      # (k x m): u_q[:, :k].T
+    v_idx.append((v_off[q] + b[:, None] * n_ + np.arange(n_)[None, :]).ravel())      # (k x n): vh_q[:k, :]
+    s_idx.append(s_off[q] + b)
+    bond_q.append(np.full(k, qn[q], dtype=np.int64))
+  ktot = int(np.sum(kept)) if kept else 0
+  cat = lambda xs: np.concatenate(xs) if xs else np.zeros(0, dtype=np.int64)
+
+  def take(buf, idx, out_code):
+    out = be._new((len(idx),), out_code)  # pylint: disable=protected-access
+    if len(idx):
+      L.check(be.lib.tnb200_gather(buf.t.data_ptr(), up(idx).data_ptr(), out.t.data_ptr(), len(idx), out_code, 0, st))
+    return out
+  u_data = take(u_buf, cat(u_idx), code)
+  v_data = take(v_buf, cat(v_idx), code)
+  s_vals = take(s_buf, cat(s_idx), T.real_code(code))
+  mod = tensor.indices[0].modulus if tensor.indices else None
+  bond_charges = cat(bond_q)
+  left = [tensor.indices[tensor.order[i]] for i in range(nl)]
+  right = [tensor.indices[tensor.order[i]] for i in range(nl, tensor.ndim)]
+  bond_u = Index(bond_charges, True, mod)
+  bond_v = Index(bond_charges, False, mod)
+  U = BlockSparseTensor(u_data, [bond_u] + left, list(range(1, nl + 1)) + [0], be)
+  V = BlockSparseTensor(v_data, [bond_v] + right, None, be)
+  assert u_data.size == BlockSparseTensor._nnz([bond_u] + left) and v_data.size == BlockSparseTensor._nnz([bond_v] + right)  # pylint: disable=protected-access
+  s_disc = np.concatenate(discarded) if discarded else np.zeros(0)
+  return U, dict(values=s_vals, index=bond_u, kept=kept, ktot=ktot), V, s_disc

@@ -612,6 +612,21 @@ static int sum_axes_t(const void* a, void* c, const ModeList& keep, const ModeLi
   return 0;
 }
 
+template <typename T>
+__global__ void gather_kernel(const T* __restrict__ src, const long long* __restrict__ idx, T* __restrict__ dst, int64_t n, int scatter) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (scatter) dst[idx[i]] = src[i]; else dst[i] = src[idx[i]];
+  }
+}
+template <typename T>
+static int gather_t(const void* src, const int64_t* idx, void* dst, int64_t n, int scatter, cudaStream_t st) {
+  if (n == 0) return 0;
+  gather_kernel<T><<<grid_for(n), 256, 0, st>>>((const T*)src, (const long long*)idx, (T*)dst, n, scatter);
+  TNB_LAUNCH_CHECK();
+  count_launch();
+  return 0;
+}
+
 static int real_dtype(int dt) {
   if (dt == TNB200_C128) return TNB200_F64;
   if (dt == TNB200_C64) return TNB200_F32;
@@ -739,6 +754,11 @@ int32_t tnb200_sum(const tnb200_tensor_t* a, const tnb200_tensor_t* c, int32_t n
   }
   merge_modes(keep, 2); merge_modes(rm, 1);
   TNB_DISPATCH_DTYPE(a->dtype, sum_axes_t, a->data, c->data, keep, rm, 0, (cudaStream_t)stream);
+}
+
+int32_t tnb200_gather(const void* src, const int64_t* idx_dev, void* dst, int64_t n, int32_t dtype, int32_t scatter, void* stream) {
+  TNB_REQUIRE(n >= 0 && (n == 0 || (src && idx_dev && dst)), TNB200_ERR_INVALID, "gather: invalid arguments");
+  TNB_DISPATCH_DTYPE(dtype, gather_t, src, idx_dev, dst, n, scatter, (cudaStream_t)stream);
 }
 
 int32_t tnb200_trace(const tnb200_tensor_t* a, const tnb200_tensor_t* c, int64_t offset, int32_t axis1, int32_t axis2, void* stream) {

@@ -54,3 +54,64 @@ def test_dense_equivalence_random(dtype):
   assert abs(ip.todense() - np.vdot(A.todense(), A.todense())) < tol * abs(np.vdot(A.todense(), A.todense())) + 1e-12
   with pytest.raises(ValueError):
     bs.tensordot(A, B, ([2, 1], [0, 1]))
+
+
+def test_golden_symmetric_svd():
+  """backends/symmetric/decompositions.py:27-216: kept / discarded singular values (sector-major order,
+  cross-sector truncation) equal the reference's; U S V reconstructs the reference's truncated tensor."""
+  be = get_backend()
+  meta, z = load_golden("symsvd")
+  for ci, m in enumerate(meta):
+    legs = [bs.Index(z["c%d_q%d" % (ci, li)], f) for li, f in enumerate(m["flows"])]
+    A = bs.BlockSparseTensor.from_data(z["c%d_A" % ci], legs, backend=be)
+    U, S, V, Sd = bs.svd(A, m["pivot"], **m["kwargs"])
+    ref_s = z["c%d_S" % ci]
+    got_s = S["values"].to_host()
+    assert got_s.shape == ref_s.shape, "case %d kept count %s vs %s" % (ci, got_s.shape, ref_s.shape)   # integer: bit exact
+    assert S["ktot"] == m["k"]
+    np.testing.assert_allclose(got_s, ref_s, atol=1e-10 * max(1.0, ref_s.max() if ref_s.size else 1.0))
+    np.testing.assert_allclose(np.sort(Sd), np.sort(z["c%d_Sdisc" % ci]), atol=1e-10)
+    ud, vd = U.todense(), V.todense()
+    assert ud.shape[-1] == m["k"] and vd.shape[0] == m["k"]
+    rec = np.tensordot(ud * got_s, vd, 1)
+    assert rel_err(rec, z["c%d_rec" % ci]) < 1e-9, "case %d" % ci
+    # isometries
+    k = m["k"]
+    u2 = ud.reshape(-1, k)
+    np.testing.assert_allclose(u2.T @ u2, np.eye(k), atol=1e-10)
+
+
+def test_batched_small_svd_direct():
+  """tnb200_svd_batched on ragged problems (tall, wide, odd sizes, complex) vs numpy."""
+  import torch
+  from tensornetwork_b200 import _lib as L
+  be = get_backend()
+  rng = np.random.default_rng(43)
+  for dtype, code, rcode, tol in (("float64", L.F64, L.F64, 1e-11), ("complex128", L.C128, L.F64, 1e-11), ("float32", L.F32, L.F32, 2e-5)):
+    shapes = [(5, 9), (9, 5), (1, 4), (7, 7), (33, 20), (20, 33), (2, 2), (64, 17)]
+    mats = []
+    for (m_, n_) in shapes:
+      x = rng.standard_normal((m_, n_))
+      if dtype.startswith("complex"):
+        x = x + 1j * rng.standard_normal((m_, n_))
+      mats.append(x.astype(dtype))
+    rs = [min(s) for s in shapes]
+    a_off = np.insert(np.cumsum([m_ * n_ for m_, n_ in shapes]), 0, 0)
+    u_off = np.insert(np.cumsum([s[0] * r for s, r in zip(shapes, rs)]), 0, 0)
+    s_off = np.insert(np.cumsum(rs), 0, 0)
+    v_off = np.insert(np.cumsum([r * s[1] for s, r in zip(shapes, rs)]), 0, 0)
+    a = be.convert_to_tensor(np.concatenate([x.ravel() for x in mats]))
+    u = be._new((int(u_off[-1]),), code); sv = be._new((int(s_off[-1]),), rcode); vh = be._new((int(v_off[-1]),), code)
+    up = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.int64)).to(be.device)
+    d = [up(np.array(shapes).ravel()), up(a_off), up(u_off), up(s_off), up(v_off)]
+    st = torch.zeros(1, dtype=torch.int32, device=be.device)
+    L.check(be.lib.tnb200_svd_batched(a.t.data_ptr(), code, len(shapes), d[0].data_ptr(), d[1].data_ptr(), u.t.data_ptr(), d[2].data_ptr(),
+                                      sv.t.data_ptr(), d[3].data_ptr(), vh.t.data_ptr(), d[4].data_ptr(), 64, 33, st.data_ptr(), be._stream()))
+    assert int(st.item()) == 0
+    uh, sh, vhh = u.to_host(), sv.to_host(), vh.to_host()
+    for q, (x, (m_, n_), r) in enumerate(zip(mats, shapes, rs)):
+      U = uh[u_off[q]:u_off[q + 1]].reshape(m_, r); S = sh[s_off[q]:s_off[q + 1]]; Vh = vhh[v_off[q]:v_off[q + 1]].reshape(r, n_)
+      ref = np.linalg.svd(x.astype(np.complex128 if dtype.startswith("complex") else np.float64), compute_uv=False)
+      np.testing.assert_allclose(S, ref, atol=tol * ref[0])
+      assert rel_err((U * S) @ Vh, x) < 50 * tol
+      np.testing.assert_allclose(U.conj().T @ U, np.eye(r), atol=200 * tol)
