@@ -26,6 +26,7 @@ struct GemmProblem {
   void* C = nullptr; int64_t c_sm = 0, c_sn = 0, c_sb = 0;
   bool conjA = false, conjB = false;
   int math = 0;  // TNB200_MATH_* >> 4
+  bool swapped = false;   // internal: operands exchanged by gemm_tcgen05 (C is written transposed)
 };
 
 // Each returns TNB200_ERR_UNSUPPORTED (without setting an error) when the problem does not

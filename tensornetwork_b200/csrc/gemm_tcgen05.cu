@@ -105,7 +105,9 @@ struct TcParams {
   //                     (MN-major) [f_in, k_in, k_out, f_out, batch]
   uint32_t a_fe, a_ke, b_fe, b_ke;
   uint32_t idesc;
-  void* C; int64_t c_sm, c_sb;        // c_sn == 1
+  void* C; int64_t c_sm, c_sb;        // row stride / batch stride of the output tile rows
+  int64_t c_cs;                       // column stride: 1 (normal) or the original row stride (swap-AB: the
+                                      // kernel computes C^T tiles and stores them transposed)
   int vec_ok;
 };
 
@@ -310,7 +312,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t r[32];
         tmem_ld32(taddr0 + j * 32, r);
         const int64_t col0 = n0 + j * 32;
-        if (row < p.M && col0 < p.N) {
+        if (p.c_cs != 1) {
+          // swap-AB: this lane's row is an ORIGINAL column; consecutive lanes -> consecutive addresses
+          if (row < p.M) {
+            const int ncol = (p.N - col0) >= 32 ? 32 : (int)(p.N - col0 > 0 ? p.N - col0 : 0);
+            const int64_t base = bi * p.c_sb + row * p.c_sm + col0 * p.c_cs;
+            if (p.out_kind == 2) {
+              float* dst = (float*)p.C + base;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) if (c < ncol) dst[(int64_t)c * p.c_cs] = __uint_as_float(r[c]);
+            } else {
+              uint16_t* dst = (uint16_t*)p.C + base;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) if (c < ncol) {
+                const float v = __uint_as_float(r[c]);
+                uint16_t h;
+                if (p.out_kind == 0) { __nv_bfloat16 b = __float2bfloat16_rn(v); h = *(uint16_t*)&b; }
+                else { __half b = __float2half_rn(v); h = *(uint16_t*)&b; }
+                dst[(int64_t)c * p.c_cs] = h;
+              }
+            }
+          }
+        } else if (row < p.M && col0 < p.N) {
           const int64_t off = bi * p.c_sb + row * p.c_sm + col0;
           const int ncol = (p.N - col0) >= 32 ? 32 : (int)(p.N - col0);
           if (p.out_kind == 2) {
@@ -655,15 +678,31 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
     if (disabled) return TNB200_ERR_UNSUPPORTED;
   }
   if (g.conjA || g.conjB) return TNB200_ERR_UNSUPPORTED;
-  if (g.c_sn != 1 && g.N > 1) return TNB200_ERR_UNSUPPORTED;
+  if (!g.swapped && g.c_sn != 1 && g.N > 1) return TNB200_ERR_UNSUPPORTED;
+  if (g.swapped && g.c_sm != 1 && g.M > 1) return TNB200_ERR_UNSUPPORTED;
   if (g.M >= (1LL << 31) || g.N >= (1LL << 31) || g.K >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
   if (!tcgen05_view_ok(g.dtype, g.A, g.M, g.K, g.batch) || !tcgen05_view_ok(g.dtype, g.B, g.N, g.K, g.batch))
     return TNB200_ERR_UNSUPPORTED;
+  // swap-AB: a tiny M under a large N would waste the 128-row MMA; compute C^T = B^T A^T instead
+  // (the big free dimension rides the 128 tile rows, the tiny one a 32/64-column tile) and let the
+  // epilogue store the tile transposed — lanes then write consecutive addresses.
+  if (g.M <= 64 && g.N >= 128 && !g.swapped) {
+    GemmProblem t = g;
+    t.swapped = true;
+    t.M = g.N; t.N = g.M; t.A = g.B; t.B = g.A;
+    t.c_sm = g.c_sn; t.c_sn = g.c_sm;          // row stride of C^T = column stride of C (1)
+    return gemm_tcgen05(t, st);
+  }
   const int es = es_of(g.dtype);
   const int sms = num_sms();
   const int64_t tiles_m = (g.M + kBM - 1) / kBM;
   int BN = 64;   // multiples of 64 so that an MN-major B tile is a whole number of 128-byte chunks
-  {
+  if (g.swapped) {
+    // tiny N: 32 columns suffice unless the (MN-major) B tile needs whole 128-byte chunks
+    const bool b_unit_f = g.B.nF == 0 || g.B.fs[g.B.nF - 1] == 1;
+    const bool b_unit_k = g.K == 1 || g.B.nK == 0 || g.B.ks[g.B.nK - 1] == 1;
+    BN = (g.N <= 32 && (b_unit_k || (b_unit_f && es == 4))) ? 32 : 64;
+  } else {
     const int cands[3] = {256, 128, 64};
     for (int i = 0; i < 3; ++i) {
       int bn = cands[i];
@@ -676,7 +715,7 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
   static int force2 = -2;
   if (force2 == -2) { const char* e = getenv("TNB200_2CTA"); force2 = e ? (e[0] == '0' ? 0 : 1) : -1; }
   bool use2 = false;
-  if (g.M >= 256 && BN >= 128) {
+  if (g.M >= 256 && BN >= 128 && !g.swapped) {
     const int64_t pair_tiles = ((g.M + 2 * kBM - 1) / (2 * kBM)) * ((g.N + BN - 1) / BN) * g.batch;
     use2 = force2 == 1 || (force2 == -1 && BN == 256 && pair_tiles >= sms / 2);
   }
@@ -696,8 +735,9 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
   if (stages > p.num_kb + 1 && p.num_tiles <= sms) stages = p.num_kb + 1 > 2 ? p.num_kb + 1 : 2;
   p.stages = stages;
   p.out_kind = g.dtype == TNB200_BF16 ? 0 : (g.dtype == TNB200_F16 ? 1 : 2);
-  p.C = g.C; p.c_sm = g.c_sm; p.c_sb = g.c_sb;
-  p.vec_ok = (((uintptr_t)g.C) % 16 == 0) && ((g.c_sm * es) % 16 == 0) && ((g.c_sb * es) % 16 == 0);
+  p.C = g.C; p.c_sm = g.c_sm; p.c_sb = g.c_sb; p.c_cs = g.swapped ? g.c_sn : 1;
+  if (g.swapped && p.c_cs == 1) p.c_cs = 2;   // degenerate (M == 1): force the transposed-store path; stride unused
+  p.vec_ok = !g.swapped && (((uintptr_t)g.C) % 16 == 0) && ((g.c_sm * es) % 16 == 0) && ((g.c_sb * es) % 16 == 0);
   CUtensorMap tmA, tmB;
   bool a_mn = false, b_mn = false;
   int rc = encode_operand(&tmA, g.dtype, g.A, g.M, g.K, g.batch, kBM, a_mn, p.a_fe, p.a_ke);

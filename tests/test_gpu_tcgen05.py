@@ -125,3 +125,25 @@ def test_multimode_operands_are_fused_not_repacked(dtype):
   out = be._contract(Ab, Bb, [1, 2], [3, 1], [0], [0])
   ref = np.einsum("bimk,bmji->bkj", ab, bb)
   assert rel_err(out.to_host(), ref) < TOLS[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float32"])
+def test_swap_ab_tiny_m(dtype):
+  """tiny M under a huge N (the ramp-up steps of the cfg-2 path): computed as C^T tiles, stored transposed."""
+  be = get_backend()
+  rng = np.random.default_rng(27)
+  for (m, k, n) in [(4, 4, 4096), (8, 8, 2048), (16, 16, 1024), (33, 40, 640), (64, 64, 512), (1, 128, 256), (2, 512, 128)]:
+    A, a = _mk(be, rng, (m, k), dtype)
+    B, b = _mk(be, rng, (k, n), dtype)
+    out = be.tensordot(A, B, 1)
+    assert be.lib.tnb200_last_kernel().decode().startswith("tcgen05"), (m, k, n)
+    assert rel_err(out.to_host(), a @ b) < TOLS[dtype], (m, k, n)
+    Bt, bt = _mk(be, rng, (n, k), dtype)          # K-major big operand
+    out = be.tensordot(A, be.transpose(Bt), 1)
+    assert rel_err(out.to_host(), a @ bt.T) < TOLS[dtype], (m, k, n)
+  # batched ramp-up step with many small legs: (nb, 4, 2, 2) . (nb, 2, 4, 2, 2, 2, 64, 2, 2) over A[1] <-> B[2]... cfg-2 style
+  Ab, ab = _mk(be, rng, (3, 8, 2, 4), dtype)
+  Bb, bb = _mk(be, rng, (3, 2, 8, 2, 2, 2, 2, 64, 2, 2), dtype)
+  out = be._contract(Ab, Bb, [1], [2], [0], [0])
+  ref = np.einsum("bkpq,bxkcdefghi->bpqxcdefghi", ab, bb)
+  assert rel_err(out.to_host(), ref) < TOLS[dtype]
