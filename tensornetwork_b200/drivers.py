@@ -17,6 +17,7 @@ a cached plan is a straight loop of kernel launches with no Python list surgery,
 what makes CUDA-graph capture of a whole network possible (graph.py).
 """
 import numpy as np
+from .tensor import B200Tensor
 
 _PLAN_CACHE = {}
 
@@ -375,6 +376,7 @@ class CompiledNetwork:
   def __init__(self, backend, shapes, dtype, labels, out_labels=(), path=None, nbatch=0,
                algorithm=None, num_streams=4):
     from . import tensor as T  # pylint: disable=import-outside-toplevel
+    from .tensor import B200Tensor  # pylint: disable=import-outside-toplevel
     self.backend = backend
     self.nbatch = nbatch
     torch = backend.torch
@@ -386,9 +388,23 @@ class CompiledNetwork:
     self.path = path
     self.steps, self.res_slot = plan_path([tuple(s) for s in shapes], labels, path,
                                           list(out_labels), nbatch)
-    self.inputs = [backend._new(s, code) for s in shapes]  # pylint: disable=protected-access
-    for t in self.inputs:
-      backend.lib.tnb200_fill(t.ref(), 0.0, 0.0, backend._stream())  # pylint: disable=protected-access
+    # all static inputs live in ONE device arena (256-byte aligned slots) mirrored by ONE pinned host
+    # staging arena, so a step's host->device transfer is a single cudaMemcpyAsync
+    tdt = T.code_to_torch(code)
+    esz = torch.empty((), dtype=tdt).element_size()
+    offs, tot = [], 0
+    for shp in shapes:
+      n = int(np.prod(shp)) if len(shp) else 1
+      offs.append(tot)
+      tot += (n * esz + 255) // 256 * 256
+    self._arena = torch.zeros(max(tot, 256), dtype=torch.uint8, device=backend.device)
+    self._host_arena = None
+    self._offs, self._esz, self._tdt, self._shapes = offs, esz, tdt, [tuple(s) for s in shapes]
+    self.inputs = []
+    for shp, off in zip(shapes, offs):
+      n = int(np.prod(shp)) if len(shp) else 1
+      view = self._arena[off:off + n * esz].view(tdt).view(tuple(shp))
+      self.inputs.append(B200Tensor(view, code))
     self.num_pairwise = len(path)
     # warm-up on a side stream (loads kernels, sets function attributes), then capture
     side = torch.cuda.Stream()
@@ -409,9 +425,26 @@ class CompiledNetwork:
         self.output = execute_plan(backend, self.inputs, self.steps, self.res_slot)
     self.launches_per_replay = int(backend.lib.tnb200_launch_count() - l0)
 
+  def host_staging(self):
+    """Pinned host views (one torch tensor per input) carved from a single staging arena.  Fill them
+    in place, then call `run_staged()`: the whole step's input moves with ONE host->device copy."""
+    torch = self.backend.torch
+    if self._host_arena is None:
+      self._host_arena = torch.zeros(self._arena.numel(), dtype=torch.uint8).pin_memory()
+      self._host_views = []
+      for shp, off in zip(self._shapes, self._offs):
+        n = int(np.prod(shp)) if len(shp) else 1
+        self._host_views.append(self._host_arena[off:off + n * self._esz].view(self._tdt).view(shp))
+    return self._host_views
+
+  def run_staged(self):
+    """one H2D of the staging arena + graph replay"""
+    self._arena.copy_(self._host_arena, non_blocking=True)
+    self.graph.replay()
+    return self.output
+
   def load(self, tensors):
     """copy inputs (B200Tensor, torch tensors or pinned host tensors) into the static buffers"""
-    from .tensor import B200Tensor  # pylint: disable=import-outside-toplevel
     for dst, src in zip(self.inputs, tensors):
       t = src.t if isinstance(src, B200Tensor) else src
       dst.t.copy_(t, non_blocking=True)

@@ -150,9 +150,34 @@ def test_skinny_long_k_uses_split_k():
     a = rng.standard_normal((2, 262144)).astype(dtype)
     b = rng.standard_normal((262144, 2)).astype(dtype)
     out = be.tensordot(be.convert_to_tensor(a), be.convert_to_tensor(b), 1)
-    assert be.lib.tnb200_last_kernel().decode() == "simt_splitk"
+    assert be.lib.tnb200_last_kernel().decode() == "skinny_dot"
     assert_close(out, a.astype(np.float64) @ b.astype(np.float64), tol=tol)
   x = rng.standard_normal((3, 5, 40000))
   y = rng.standard_normal((40000, 5, 7))
   assert_close(be.tensordot(be.convert_to_tensor(x), be.convert_to_tensor(y), ([2, 1], [0, 1])),
                np.tensordot(x, y, ([2, 1], [0, 1])), tol=1e-10)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_skinny_outer_family(dtype):
+  """one side tiny + short K, other side long (cfg-2 ramp-up steps), incl. many-leg operands and batch."""
+  be = get_backend()
+  rng = np.random.default_rng(7)
+  tol = 1e-10 if dtype == "float64" else 2e-5
+  a = rng.standard_normal((2, 2, 4)).astype(dtype)
+  b = rng.standard_normal((4, 2, 2, 2, 2, 2, 64, 2, 2)).astype(dtype)
+  out = be.tensordot(be.convert_to_tensor(a), be.convert_to_tensor(b), ([2], [0]))
+  assert be.lib.tnb200_last_kernel().decode() == "skinny_outer"
+  assert_close(out, np.tensordot(a.astype(np.float64), b.astype(np.float64), ([2], [0])), tol=tol)
+  # mirrored: the long operand first, contracted over an inner axis of both
+  c = rng.standard_normal((2, 2, 2, 2, 512, 2, 2)).astype(dtype)
+  d = rng.standard_normal((2, 2)).astype(dtype)
+  out = be.tensordot(be.convert_to_tensor(c), be.convert_to_tensor(d), ([0], [0]))
+  assert be.lib.tnb200_last_kernel().decode() == "skinny_outer"
+  assert_close(out, np.tensordot(c.astype(np.float64), d.astype(np.float64), ([0], [0])), tol=tol)
+  # batched + transposed view of the long operand
+  A = rng.standard_normal((5, 3, 6)).astype(dtype)
+  B = rng.standard_normal((5, 2048, 6)).astype(dtype)
+  out = be._contract(be.convert_to_tensor(A), be.convert_to_tensor(B), [2], [2], [0], [0])
+  assert be.lib.tnb200_last_kernel().decode() == "skinny_outer"
+  assert_close(out, np.einsum("bmk,bnk->bmn", A.astype(np.float64), B.astype(np.float64)), tol=tol)
