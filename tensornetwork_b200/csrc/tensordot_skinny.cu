@@ -27,7 +27,7 @@ struct SkinnyParams {
   int S, K;
 };
 
-template <typename T, typename Acc>
+template <typename T, typename Acc, int VEC>
 __global__ void __launch_bounds__(256) skinny_outer_kernel(const __grid_constant__ SkinnyParams<T> p) {
   __shared__ Acc sh[SK_MAXS][SK_MAXK];          // the tiny operand, one batch entry
   __shared__ long long kofs[SK_MAXK];           // long-operand offset of each k
@@ -45,21 +45,36 @@ __global__ void __launch_bounds__(256) skinny_outer_kernel(const __grid_constant
   for (int k = threadIdx.x; k < p.K; k += blockDim.x) { int64_t a, b; mode_offsets(p.mK, k, a, b); kofs[k] = a; }
   for (int s = threadIdx.x; s < p.S; s += blockDim.x) { int64_t a, b; mode_offsets(p.mS, s, a, b); sofs[s] = b; }
   __syncthreads();
-  for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < p.L; l += (int64_t)gridDim.x * blockDim.x) {
+  // each thread owns VEC consecutive elements of the long side (VEC > 1 only when the innermost long
+  // mode is unit-stride in both the operand and C and VEC divides its extent: 16-byte loads / stores)
+  struct alignas(sizeof(T) * VEC) Pack { T v[VEC]; };
+  const int64_t nvec = p.L / VEC;
+  for (int64_t lv = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; lv < nvec; lv += (int64_t)gridDim.x * blockDim.x) {
     int64_t ol, oc;
-    mode_offsets(p.mL, l, ol, oc);
+    mode_offsets(p.mL, lv * VEC, ol, oc);
     const T* src = p.Lp + offLb + ol;
-    Acc acc[SK_MAXS];
+    Acc acc[SK_MAXS][VEC];
 #pragma unroll
-    for (int s = 0; s < SK_MAXS; ++s) acc[s] = acc_zero((Acc*)nullptr);
+    for (int s = 0; s < SK_MAXS; ++s)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[s][v] = acc_zero((Acc*)nullptr);
     for (int k = 0; k < p.K; ++k) {
-      const Acc x = to_acc(src[kofs[k]]);
+      const Pack x = *reinterpret_cast<const Pack*>(src + kofs[k]);
 #pragma unroll
-      for (int s = 0; s < SK_MAXS; ++s) if (s < p.S) fma_acc(acc[s], x, sh[s][k]);
+      for (int s = 0; s < SK_MAXS; ++s) if (s < p.S) {
+        const Acc w = sh[s][k];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) fma_acc(acc[s][v], to_acc(x.v[v]), w);
+      }
     }
     T* dst = p.C + offCb + oc;
 #pragma unroll
-    for (int s = 0; s < SK_MAXS; ++s) if (s < p.S) dst[sofs[s]] = FromAcc<T, Acc>::f(acc[s]);
+    for (int s = 0; s < SK_MAXS; ++s) if (s < p.S) {
+      Pack o;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o.v[v] = FromAcc<T, Acc>::f(acc[s][v]);
+      *reinterpret_cast<Pack*>(dst + sofs[s]) = o;
+    }
   }
 }
 
@@ -68,37 +83,52 @@ struct DotParams {
   const T* A; const T* B; T* C;
   DevModes mB, mM, mN, mK;   // as in the generic kernel: mM (s0 A, s1 C), mN (s0 B, s1 C), mK (s0 A, s1 B)
   int64_t K, batch, kchunk;
-  int M, N;
+  int M, N, inner;
   void* ws;                  // [batch][M][N] accumulators
 };
+
+constexpr int DOT_IB = 2048;   // inner block of the contraction whose operand offsets are tabulated in smem
 
 template <typename T, typename Acc>
 __global__ void __launch_bounds__(256) skinny_dot_kernel(const __grid_constant__ DotParams<T> p) {
   __shared__ long long aofs[16], bofs[16];
+  __shared__ int ia[DOT_IB], ib[DOT_IB];         // offsets of the inner block (relative, fit in 32 bits)
   __shared__ Acc red[8][16];
   const int64_t bb = blockIdx.x;
   int64_t offAb, offBb, offCb;
   mode_offsets3(p.mB, bb, offAb, offBb, offCb);
   if (threadIdx.x < p.M) { int64_t a, c; mode_offsets(p.mM, threadIdx.x, a, c); aofs[threadIdx.x] = a; }
   if (threadIdx.x < p.N) { int64_t b, c; mode_offsets(p.mN, threadIdx.x, b, c); bofs[threadIdx.x] = b; }
+  const int inner = p.inner;                     // product of the trailing K modes (<= DOT_IB), divides K
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+    int64_t oa, ob;
+    mode_offsets(p.mK, i, oa, ob);               // i < inner only touches the trailing modes
+    ia[i] = (int)oa; ib[i] = (int)ob;
+  }
   __syncthreads();
   Acc acc[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) acc[i] = acc_zero((Acc*)nullptr);
-  const int64_t k0 = (int64_t)blockIdx.y * p.kchunk;
-  const int64_t k1 = k0 + p.kchunk < p.K ? k0 + p.kchunk : p.K;
-  for (int64_t k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+  const int64_t nouter = p.K / inner;
+  const int64_t o0 = (int64_t)blockIdx.y * p.kchunk;            // kchunk counts OUTER indices here
+  const int64_t o1 = o0 + p.kchunk < nouter ? o0 + p.kchunk : nouter;
+  for (int64_t o = o0; o < o1; ++o) {
     int64_t oa, ob;
-    if (p.mK.n <= 1) { oa = k * p.mK.s0[0]; ob = k * p.mK.s1[0]; } else mode_offsets(p.mK, k, oa, ob);
-    Acc a[4], b[4];
+    mode_offsets(p.mK, o * inner, oa, ob);       // offsets of the outer K modes (uniform across the CTA)
+    const T* Ap = p.A + offAb + oa;
+    const T* Bp = p.B + offBb + ob;
+    for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+      const int xa = ia[i], xb = ib[i];
+      Acc a[4], b[4];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) a[m] = m < p.M ? to_acc(p.A[offAb + aofs[m] + oa]) : acc_zero((Acc*)nullptr);
+      for (int m = 0; m < 4; ++m) a[m] = m < p.M ? to_acc(Ap[aofs[m] + xa]) : acc_zero((Acc*)nullptr);
 #pragma unroll
-    for (int n = 0; n < 4; ++n) b[n] = n < p.N ? to_acc(p.B[offBb + bofs[n] + ob]) : acc_zero((Acc*)nullptr);
+      for (int n = 0; n < 4; ++n) b[n] = n < p.N ? to_acc(Bp[bofs[n] + xb]) : acc_zero((Acc*)nullptr);
 #pragma unroll
-    for (int m = 0; m < 4; ++m)
+      for (int m = 0; m < 4; ++m)
 #pragma unroll
-      for (int n = 0; n < 4; ++n) fma_acc(acc[m * 4 + n], a[m], b[n]);
+        for (int n = 0; n < 4; ++n) fma_acc(acc[m * 4 + n], a[m], b[n]);
+    }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -140,10 +170,21 @@ static int run_outer(const void* Lp, const void* Sp, void* C, const ModeList& mB
   if (!to_dev(mB, p.mB) || !to_dev(mL, p.mL) || !to_dev(mS, p.mS) || !to_dev(mK, p.mK)) return TNB200_ERR_UNSUPPORTED;
   p.L = mL.total(); p.batch = mB.total(); p.S = (int)mS.total(); p.K = (int)mK.total();
   if (p.batch > 65535) return TNB200_ERR_UNSUPPORTED;
-  int64_t blocks = (p.L + 255) / 256;
+  // vector width: 16 bytes when the innermost long mode is contiguous in the operand and in C and everything is aligned
+  constexpr int VMAX = 16 / (int)sizeof(T);
+  bool vec = mL.n > 0 && mL.s0[mL.n - 1] == 1 && mL.s1[mL.n - 1] == 1 && mL.ext[mL.n - 1] % VMAX == 0 &&
+             ((uintptr_t)Lp % 16 == 0) && ((uintptr_t)C % 16 == 0);
+  auto mult = [&](int64_t x) { return x % VMAX == 0; };
+  for (int i = 0; i + 1 < mL.n && vec; ++i) vec = mult(mL.s0[i]) && mult(mL.s1[i]);
+  for (int i = 0; i < mK.n && vec; ++i) vec = mult(mK.s0[i]);
+  for (int i = 0; i < mS.n && vec; ++i) vec = mult(mS.s1[i]);
+  for (int i = 0; i < mB.n && vec; ++i) vec = mult(mB.s0[i]) && mult(mB.s2[i]);
+  const int64_t work = vec ? p.L / VMAX : p.L;
+  int64_t blocks = (work + 255) / 256;
   const int64_t cap = ((int64_t)num_sms() * 16 + p.batch - 1) / p.batch;
   if (blocks > cap) blocks = cap < 1 ? 1 : cap;
-  skinny_outer_kernel<T, Acc><<<dim3((unsigned)blocks, (unsigned)p.batch), 256, 0, st>>>(p);
+  if (vec) skinny_outer_kernel<T, Acc, VMAX><<<dim3((unsigned)blocks, (unsigned)p.batch), 256, 0, st>>>(p);
+  else skinny_outer_kernel<T, Acc, 1><<<dim3((unsigned)blocks, (unsigned)p.batch), 256, 0, st>>>(p);
   TNB_LAUNCH_CHECK();
   count_launch();
   set_kernel_name("skinny_outer");
@@ -159,11 +200,32 @@ static int run_dot(const void* A, const void* B, void* C, const ModeList& mB, co
   if (!to_dev(mB, p.mB) || !to_dev(mM, p.mM) || !to_dev(mN, p.mN) || !to_dev(mK, p.mK)) return TNB200_ERR_UNSUPPORTED;
   p.K = mK.total(); p.batch = mB.total(); p.M = (int)mM.total(); p.N = (int)mN.total();
   if (p.batch >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
+  // inner block = trailing K modes whose product stays <= DOT_IB (single-mode K: split it evenly)
+  int64_t inner = 1;
+  {
+    int i = mK.n - 1;
+    while (i >= 0 && inner * mK.ext[i] <= DOT_IB) { inner *= mK.ext[i]; --i; }
+    if (inner == 1 && mK.n > 0) {            // innermost mode alone exceeds the table: carve a divisor out of it
+      int64_t e = mK.ext[mK.n - 1], d = DOT_IB;
+      while (d > 1 && e % d) --d;
+      // represent K as (..., e/d, d): handled by pushing an extra mode into the device list below
+      inner = d;
+      if (d > 1) {
+        DevModes& k = p.mK;
+        if (k.n >= kDevModes) return TNB200_ERR_UNSUPPORTED;
+        const int last = k.n - 1;
+        k.ext[k.n] = d; k.s0[k.n] = k.s0[last]; k.s1[k.n] = k.s1[last]; k.s2[k.n] = 0;
+        k.ext[last] = e / d; k.s0[last] *= d; k.s1[last] *= d;
+        ++k.n;
+      }
+    }
+  }
+  p.inner = (int)inner;
+  const int64_t nouter = p.K / inner;
   int64_t want = ((int64_t)num_sms() * 4 + p.batch - 1) / p.batch;
-  int64_t maxs = p.K / 2048; if (maxs < 1) maxs = 1;
-  int64_t sp = want < maxs ? want : maxs; if (sp < 1) sp = 1; if (sp > 65535) sp = 65535;
-  p.kchunk = (p.K + sp - 1) / sp;
-  sp = (p.K + p.kchunk - 1) / p.kchunk;
+  int64_t sp = want < nouter ? want : nouter; if (sp < 1) sp = 1; if (sp > 65535) sp = 65535;
+  p.kchunk = (nouter + sp - 1) / sp;
+  sp = (nouter + p.kchunk - 1) / p.kchunk;
   const size_t bytes = sizeof(Acc) * (size_t)(p.batch * p.M * p.N);
   int rc = ws_alloc(&p.ws, bytes, st);
   if (rc) return rc;

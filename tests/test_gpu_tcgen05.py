@@ -136,7 +136,8 @@ def test_swap_ab_tiny_m(dtype):
     A, a = _mk(be, rng, (m, k), dtype)
     B, b = _mk(be, rng, (k, n), dtype)
     out = be.tensordot(A, B, 1)
-    assert be.lib.tnb200_last_kernel().decode().startswith("tcgen05"), (m, k, n)
+    kern = be.lib.tnb200_last_kernel().decode()     # short K + tiny M streams through the CUDA-core kernel
+    assert kern.startswith("tcgen05") or kern == "skinny_outer", (m, k, n, kern)
     assert rel_err(out.to_host(), a @ b) < TOLS[dtype], (m, k, n)
     Bt, bt = _mk(be, rng, (n, k), dtype)          # K-major big operand
     out = be.tensordot(A, be.transpose(Bt), 1)
