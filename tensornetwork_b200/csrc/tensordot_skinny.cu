@@ -58,13 +58,19 @@ __global__ void __launch_bounds__(256) skinny_outer_kernel(const __grid_constant
     for (int s = 0; s < SK_MAXS; ++s)
 #pragma unroll
       for (int v = 0; v < VEC; ++v) acc[s][v] = acc_zero((Acc*)nullptr);
-    for (int k = 0; k < p.K; ++k) {
-      const Pack x = *reinterpret_cast<const Pack*>(src + kofs[k]);
+    // 4 independent loads in flight per thread before any of them is consumed (latency hiding)
+    for (int k0 = 0; k0 < p.K; k0 += 4) {
+      Pack x[4];
 #pragma unroll
-      for (int s = 0; s < SK_MAXS; ++s) if (s < p.S) {
-        const Acc w = sh[s][k];
+      for (int j = 0; j < 4; ++j) if (k0 + j < p.K) x[j] = *reinterpret_cast<const Pack*>(src + kofs[k0 + j]);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) fma_acc(acc[s][v], to_acc(x.v[v]), w);
+      for (int j = 0; j < 4; ++j) if (k0 + j < p.K) {
+#pragma unroll
+        for (int s = 0; s < SK_MAXS; ++s) if (s < p.S) {
+          const Acc w = sh[s][k0 + j];
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) fma_acc(acc[s][v], to_acc(x[j].v[v]), w);
+        }
       }
     }
     T* dst = p.C + offCb + oc;
@@ -171,7 +177,8 @@ static int run_outer(const void* Lp, const void* Sp, void* C, const ModeList& mB
   p.L = mL.total(); p.batch = mB.total(); p.S = (int)mS.total(); p.K = (int)mK.total();
   if (p.batch > 65535) return TNB200_ERR_UNSUPPORTED;
   // vector width: 16 bytes when the innermost long mode is contiguous in the operand and in C and everything is aligned
-  constexpr int VMAX = 16 / (int)sizeof(T);
+  // <= 4 elements per thread: S * VEC accumulators must stay in registers (16 x 8 floats spilled)
+  constexpr int VMAX = (16 / (int)sizeof(T)) > 4 ? 4 : (16 / (int)sizeof(T));
   bool vec = mL.n > 0 && mL.s0[mL.n - 1] == 1 && mL.s1[mL.n - 1] == 1 && mL.ext[mL.n - 1] % VMAX == 0 &&
              ((uintptr_t)Lp % 16 == 0) && ((uintptr_t)C % 16 == 0);
   auto mult = [&](int64_t x) { return x % VMAX == 0; };

@@ -193,3 +193,51 @@ def contract_tree_parallel(tensors, labels, out_labels, path, rank, world, contr
   root_rank = owner[-1] if ssa else 0
   res = vals.get(root, (None, None))[0] if rank == root_rank else None
   return res, root_rank, info
+
+
+# ------------------------------------------------------------------------ NCCL execution
+def contract_network_parallel(backend, tensors, labels, out_labels=(), path=None, step_flops=None, group=None):
+  """`contract_tree_parallel` on the CUDA backend with torch.distributed (NCCL over NVLink) as transport.
+  Every rank passes the same inputs (B200Tensors or host arrays); returns (result B200Tensor on the root
+  rank / None elsewhere, root_rank, info)."""
+  import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+  from . import drivers  # pylint: disable=import-outside-toplevel
+  from .tensor import B200Tensor  # pylint: disable=import-outside-toplevel
+  rank, world = dist.get_rank(group), dist.get_world_size(group)
+  ts = [backend.convert_to_tensor(t) for t in tensors]
+  sizes = {l: t.shape[ax] for t, labs in zip(ts, labels) for ax, l in enumerate(labs)}
+  if path is None:
+    path = drivers.greedy_path(labels, out_labels, sizes)
+  n = len(ts)
+  ssa = path_to_ssa(n, path)
+  lab = {i: list(l) for i, l in enumerate(labels)}
+  flops = []
+  for a, b, o in ssa:
+    shared = [l for l in lab[a] if l in lab[b]]
+    lab[o] = [l for l in lab[a] if l not in shared] + [l for l in lab[b] if l not in shared]
+    k = float(np.prod([sizes[l] for l in shared])) if shared else 1.0
+    flops.append(2.0 * k * float(np.prod([sizes[l] for l in lab[o]] or [1.0])))
+  if step_flops is None:
+    step_flops = flops
+  code = ts[0].code
+
+  def pair(t1, l1, t2, l2):
+    shared = [l for l in l1 if l in l2]
+    a1 = [l1.index(l) for l in shared]
+    a2 = [l2.index(l) for l in shared]
+    srt = sorted(range(len(a1)), key=lambda i: a1[i])
+    out = backend.tensordot(t1, t2, ([a1[i] for i in srt], [a2[i] for i in srt]))
+    return out, [l for l in l1 if l not in shared] + [l for l in l2 if l not in shared]
+
+  def send(t, dst):
+    dist.send(backend.contiguous(t).t, dst, group=group)
+
+  def recv(tid, src):
+    buf = backend._new([sizes[l] for l in lab[tid]], code)  # pylint: disable=protected-access
+    dist.recv(buf.t, src, group=group)
+    return buf
+  res, root_rank, info = contract_tree_parallel(ts, labels, out_labels, path, rank, world, pair, send, recv, step_flops)
+  if res is not None and len(lab[ssa[-1][2]]) > 1 and list(out_labels):
+    final = lab[ssa[-1][2]]
+    res = backend.transpose(res, tuple(final.index(l) for l in out_labels))
+  return res, root_rank, info
