@@ -81,8 +81,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, sm_100 version = 1)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -114,6 +114,77 @@ struct TcParams {
 constexpr int kBM = 128;
 constexpr int kRowBytes = 128;        // one swizzle row = BK elements
 constexpr int kThreads = 256;
+
+
+// Store one 32-column chunk of an accumulator row held by this lane (row = TMEM lane).  Normal mode: the
+// lane's 32 values are contiguous in C (vector stores).  swap-AB (c_cs != 1): the lane's row is an ORIGINAL
+// column, so consecutive lanes write consecutive addresses (coalesced across the warp).
+__device__ __forceinline__ void epilogue_store_chunk(const TcParams& p, const uint32_t* r, int64_t bi, int64_t row, int64_t col0) {
+  if (p.c_cs != 1) {
+    if (row < p.M) {
+      const int ncol = (p.N - col0) >= 32 ? 32 : (int)(p.N - col0 > 0 ? p.N - col0 : 0);
+      const int64_t base = bi * p.c_sb + row * p.c_sm + col0 * p.c_cs;
+      if (p.out_kind == 2) {
+        float* dst = (float*)p.C + base;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) if (c < ncol) dst[(int64_t)c * p.c_cs] = __uint_as_float(r[c]);
+      } else {
+        uint16_t* dst = (uint16_t*)p.C + base;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) if (c < ncol) {
+          const float v = __uint_as_float(r[c]);
+          uint16_t h;
+          if (p.out_kind == 0) { __nv_bfloat16 b = __float2bfloat16_rn(v); h = *(uint16_t*)&b; }
+          else { __half b = __float2half_rn(v); h = *(uint16_t*)&b; }
+          dst[(int64_t)c * p.c_cs] = h;
+        }
+      }
+    }
+  } else if (row < p.M && col0 < p.N) {
+    const int64_t off = bi * p.c_sb + row * p.c_sm + col0;
+    const int ncol = (p.N - col0) >= 32 ? 32 : (int)(p.N - col0);
+    if (p.out_kind == 2) {
+      float* dst = (float*)p.C + off;
+      if (ncol == 32 && p.vec_ok) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+          ((float4*)dst)[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
+                                          __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = __uint_as_float(r[c]);
+      }
+    } else {
+      uint16_t* dst = (uint16_t*)p.C + off;
+      uint32_t pk[16];
+#pragma unroll
+      for (int v = 0; v < 16; ++v) {
+        float lo = __uint_as_float(r[2 * v]), hi = __uint_as_float(r[2 * v + 1]);
+        if (p.out_kind == 0) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); pk[v] = *(uint32_t*)&h; }
+        else { __half2 h = __floats2half2_rn(lo, hi); pk[v] = *(uint32_t*)&h; }
+      }
+      if (ncol == 32 && p.vec_ok) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) ((uint4*)dst)[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = (uint16_t)(pk[c >> 1] >> ((c & 1) * 16));
+      }
+    }
+  }
+}
+// Drain one accumulator (BN columns) of this warp's 32 TMEM lanes: two chunks are loaded per iteration into
+// separate register sets, so the tcgen05.ld of the next pair never waits on the stores of the previous one.
+__device__ __forceinline__ void epilogue_drain(const TcParams& p, uint32_t taddr0, int BN, int64_t bi, int64_t row, int64_t n0) {
+  for (int j = 0; j < BN / 32; j += 2) {
+    uint32_t ra[32], rb[32];
+    tmem_ld32(taddr0 + j * 32, ra);
+    tmem_ld32(taddr0 + (j + 1) * 32, rb);
+    tmem_ld_wait();
+    epilogue_store_chunk(p, ra, bi, row, n0 + (int64_t)j * 32);
+    epilogue_store_chunk(p, rb, bi, row, n0 + (int64_t)(j + 1) * 32);
+  }
+}
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -308,69 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      for (int j = 0; j < BN / 32; ++j) {
-        uint32_t r[32];
-        tmem_ld32(taddr0 + j * 32, r);
-        const int64_t col0 = n0 + j * 32;
-        if (p.c_cs != 1) {
-          // swap-AB: this lane's row is an ORIGINAL column; consecutive lanes -> consecutive addresses
-          if (row < p.M) {
-            const int ncol = (p.N - col0) >= 32 ? 32 : (int)(p.N - col0 > 0 ? p.N - col0 : 0);
-            const int64_t base = bi * p.c_sb + row * p.c_sm + col0 * p.c_cs;
-            if (p.out_kind == 2) {
-              float* dst = (float*)p.C + base;
-#pragma unroll
-              for (int c = 0; c < 32; ++c) if (c < ncol) dst[(int64_t)c * p.c_cs] = __uint_as_float(r[c]);
-            } else {
-              uint16_t* dst = (uint16_t*)p.C + base;
-#pragma unroll
-              for (int c = 0; c < 32; ++c) if (c < ncol) {
-                const float v = __uint_as_float(r[c]);
-                uint16_t h;
-                if (p.out_kind == 0) { __nv_bfloat16 b = __float2bfloat16_rn(v); h = *(uint16_t*)&b; }
-                else { __half b = __float2half_rn(v); h = *(uint16_t*)&b; }
-                dst[(int64_t)c * p.c_cs] = h;
-              }
-            }
-          }
-        } else if (row < p.M && col0 < p.N) {
-          const int64_t off = bi * p.c_sb + row * p.c_sm + col0;
-          const int ncol = (p.N - col0) >= 32 ? 32 : (int)(p.N - col0);
-          if (p.out_kind == 2) {
-            float* dst = (float*)p.C + off;
-            if (ncol == 32 && p.vec_ok) {
-#pragma unroll
-              for (int v = 0; v < 8; ++v)
-                ((float4*)dst)[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                                __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = __uint_as_float(r[c]);
-            }
-          } else {
-            uint16_t* dst = (uint16_t*)p.C + off;
-            uint32_t pk[16];
-#pragma unroll
-            for (int v = 0; v < 16; ++v) {
-              float lo = __uint_as_float(r[2 * v]), hi = __uint_as_float(r[2 * v + 1]);
-              if (p.out_kind == 0) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-                pk[v] = *(uint32_t*)&h;
-              } else {
-                __half2 h = __floats2half2_rn(lo, hi);
-                pk[v] = *(uint32_t*)&h;
-              }
-            }
-            if (ncol == 32 && p.vec_ok) {
-#pragma unroll
-              for (int v = 0; v < 4; ++v) ((uint4*)dst)[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = (uint16_t)(pk[c >> 1] >> ((c & 1) * 16));
-            }
-          }
-        }
-      }
+      epilogue_drain(p, taddr0, BN, bi, row, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -494,43 +503,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      for (int j = 0; j < BN / 32; ++j) {
-        uint32_t r[32];
-        tmem_ld32(taddr0 + j * 32, r);
-        const int64_t col0 = n0 + j * 32;
-        if (row < p.M && col0 < p.N) {
-          const int64_t off = bi * p.c_sb + row * p.c_sm + col0;
-          const int ncol = (p.N - col0) >= 32 ? 32 : (int)(p.N - col0);
-          if (p.out_kind == 2) {
-            float* dst = (float*)p.C + off;
-            if (ncol == 32 && p.vec_ok) {
-#pragma unroll
-              for (int v = 0; v < 8; ++v)
-                ((float4*)dst)[v] = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                                __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = __uint_as_float(r[c]);
-            }
-          } else {
-            uint16_t* dst = (uint16_t*)p.C + off;
-            uint32_t pk[16];
-#pragma unroll
-            for (int v = 0; v < 16; ++v) {
-              float lo = __uint_as_float(r[2 * v]), hi = __uint_as_float(r[2 * v + 1]);
-              if (p.out_kind == 0) { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); pk[v] = *(uint32_t*)&h; }
-              else { __half2 h = __floats2half2_rn(lo, hi); pk[v] = *(uint32_t*)&h; }
-            }
-            if (ncol == 32 && p.vec_ok) {
-#pragma unroll
-              for (int v = 0; v < 4; ++v) ((uint4*)dst)[v] = make_uint4(pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
-            } else {
-#pragma unroll
-              for (int c = 0; c < 32; ++c) if (c < ncol) dst[c] = (uint16_t)(pk[c >> 1] >> ((c & 1) * 16));
-            }
-          }
-        }
-      }
+      epilogue_drain(p, taddr0, BN, bi, row, n0);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }

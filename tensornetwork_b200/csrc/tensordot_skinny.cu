@@ -188,7 +188,9 @@ static int run_outer(const void* Lp, const void* Sp, void* C, const ModeList& mB
   for (int i = 0; i < mB.n && vec; ++i) vec = mult(mB.s0[i]) && mult(mB.s2[i]);
   const int64_t work = vec ? p.L / VMAX : p.L;
   int64_t blocks = (work + 255) / 256;
-  const int64_t cap = ((int64_t)num_sms() * 16 + p.batch - 1) / p.batch;
+  // few, fat CTAs: the per-CTA prologue (offset tables in shared memory) must be amortised over many
+  // grid-stride iterations — about 4 CTAs per SM in total
+  const int64_t cap = ((int64_t)num_sms() * 4 + p.batch - 1) / p.batch;
   if (blocks > cap) blocks = cap < 1 ? 1 : cap;
   if (vec) skinny_outer_kernel<T, Acc, VMAX><<<dim3((unsigned)blocks, (unsigned)p.batch), 256, 0, st>>>(p);
   else skinny_outer_kernel<T, Acc, 1><<<dim3((unsigned)blocks, (unsigned)p.batch), 256, 0, st>>>(p);

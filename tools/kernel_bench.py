@@ -54,6 +54,18 @@ if __name__ == "__main__":
     run(be, dt, (64, 1024, 512), (64, 512, 1024), None, reps=3, batch=True)
     run(be, dt, (512, 2, 512), (512, 2, 512), [[2], [0]], reps=3)
     sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "--stepab":
+    # eager launches of the two bulk cfg-2 steps at NB samples (for ncu --set full captures)
+    nb = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    A = tb.B200Tensor(torch.randn((nb, 512, 2, 512), device=be.device, dtype=torch.float32).to(torch.bfloat16))
+    E = tb.B200Tensor(torch.randn((nb, 512, 512), device=be.device, dtype=torch.float32).to(torch.bfloat16))
+    Tt = tb.B200Tensor(torch.randn((nb, 2, 512, 512), device=be.device, dtype=torch.float32).to(torch.bfloat16))
+    for _ in range(4):
+      be._contract(A, E, [1], [2], [0], [0])
+      be._contract(A, Tt, [1, 2], [3, 1], [0], [0])
+    torch.cuda.synchronize()
+    print("done", be.lib.tnb200_last_kernel().decode())
+    sys.exit(0)
   if len(sys.argv) > 1 and sys.argv[1] == "--svd":
     import time
     sizes = [int(x) for x in sys.argv[2:]] or [1024, 2048]
