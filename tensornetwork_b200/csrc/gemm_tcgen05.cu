@@ -173,16 +173,85 @@ __device__ __forceinline__ void epilogue_store_chunk(const TcParams& p, const ui
     }
   }
 }
-// Drain one accumulator (BN columns) of this warp's 32 TMEM lanes: two chunks are loaded per iteration into
-// separate register sets, so the tcgen05.ld of the next pair never waits on the stores of the previous one.
-__device__ __forceinline__ void epilogue_drain(const TcParams& p, uint32_t taddr0, int BN, int64_t bi, int64_t row, int64_t n0) {
+constexpr int kSlabRow = 144;                 // 128 data bytes + 16 pad: conflict-free 16-byte rows
+constexpr int kSlabBytes = 32 * kSlabRow;     // one warp's staging slab (32 accumulator rows)
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// Drain one accumulator (BN columns) of this warp's 32 TMEM lanes.
+// Fast path (row-major output, aligned, N a multiple of the 16-byte vector): 128 bytes of every row are
+// converted, staged in a per-warp shared-memory slab and written back so that 8 consecutive lanes cover one
+// row's 128 bytes — every global store instruction writes 4 full cache lines (the direct path writes
+// 32 half-empty sectors).  Two TMEM chunks are always in flight in separate register sets.
+__device__ __forceinline__ void epilogue_drain(const TcParams& p, uint32_t taddr0, int BN, int64_t bi, int64_t row0,
+                                               int lane, int64_t n0, uint32_t slab) {
+  const int64_t row = row0 + lane;
+  const int es = p.out_kind == 2 ? 4 : 2;
+  const bool staged = p.c_cs == 1 && p.vec_ok && (p.N % (16 / es) == 0);
+  if (!staged) {
+    for (int j = 0; j < BN / 32; j += 2) {
+      uint32_t ra[32], rb[32];
+      tmem_ld32(taddr0 + j * 32, ra);
+      tmem_ld32(taddr0 + (j + 1) * 32, rb);
+      tmem_ld_wait();
+      epilogue_store_chunk(p, ra, bi, row, n0 + (int64_t)j * 32);
+      epilogue_store_chunk(p, rb, bi, row, n0 + (int64_t)(j + 1) * 32);
+    }
+    return;
+  }
+  const uint32_t my_row = slab + (uint32_t)lane * kSlabRow;
+  const int cols_per_pass = 128 / es;                       // 64 (16-bit) or 32 (fp32) columns = 128 bytes per row
   for (int j = 0; j < BN / 32; j += 2) {
     uint32_t ra[32], rb[32];
     tmem_ld32(taddr0 + j * 32, ra);
     tmem_ld32(taddr0 + (j + 1) * 32, rb);
     tmem_ld_wait();
-    epilogue_store_chunk(p, ra, bi, row, n0 + (int64_t)j * 32);
-    epilogue_store_chunk(p, rb, bi, row, n0 + (int64_t)(j + 1) * 32);
+    const int npass = es == 2 ? 1 : 2;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      if (pass >= npass) break;
+      if (es == 2) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int v = 0; v < 16; ++v) {
+          float lo = __uint_as_float(ra[2 * v]), hi = __uint_as_float(ra[2 * v + 1]);
+          float lo2 = __uint_as_float(rb[2 * v]), hi2 = __uint_as_float(rb[2 * v + 1]);
+          if (p.out_kind == 0) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); pk[v] = *(uint32_t*)&h;
+            __nv_bfloat162 g = __floats2bfloat162_rn(lo2, hi2); pk[16 + v] = *(uint32_t*)&g;
+          } else {
+            __half2 h = __floats2half2_rn(lo, hi); pk[v] = *(uint32_t*)&h;
+            __half2 g = __floats2half2_rn(lo2, hi2); pk[16 + v] = *(uint32_t*)&g;
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) st_shared_v4(my_row + v * 16, pk[4 * v], pk[4 * v + 1], pk[4 * v + 2], pk[4 * v + 3]);
+      } else {
+        const uint32_t* r = pass == 0 ? ra : rb;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) st_shared_v4(my_row + v * 16, r[4 * v], r[4 * v + 1], r[4 * v + 2], r[4 * v + 3]);
+      }
+      __syncwarp();
+      const int64_t col0 = n0 + (int64_t)j * 32 + (es == 2 ? 0 : pass * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = lane + 32 * i, r = c >> 3, part = c & 7;
+        const uint4 v = ld_shared_v4(slab + (uint32_t)r * kSlabRow + (uint32_t)part * 16);
+        const int64_t grow = row0 + r, gcol = col0 + (int64_t)part * (16 / es);
+        if (grow < p.M && gcol < p.N) {
+          char* dst = (char*)p.C + (bi * p.c_sb + grow * p.c_sm + gcol) * es;
+          *(uint4*)dst = v;
+        }
+      }
+      __syncwarp();
+    }
   }
 }
 
@@ -304,6 +373,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+  const uint32_t epi_slab = (smem_u32(tmem_slot) + 16 + 15) & ~15u;   // 4 warps x kSlabBytes of epilogue staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -379,7 +449,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      epilogue_drain(p, taddr0, BN, bi, row, n0);
+      epilogue_drain(p, taddr0, BN, bi, row - lane, lane, n0, epi_slab + (uint32_t)q * kSlabBytes);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -426,6 +496,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+  const uint32_t epi_slab = (smem_u32(tmem_slot) + 16 + 15) & ~15u;   // 4 warps x kSlabBytes of epilogue staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -503,7 +574,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
-      epilogue_drain(p, taddr0, BN, bi, row, n0);
+      epilogue_drain(p, taddr0, BN, bi, row - lane, lane, n0, epi_slab + (uint32_t)q * kSlabBytes);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }
@@ -703,7 +774,7 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
   p.num_tiles = p.tiles_m * p.tiles_n * g.batch;
   const int b_rows = use2 ? BN / 2 : BN;                   // B rows staged per CTA per k-block
   const int stage_bytes = kBM * kRowBytes + b_rows * kRowBytes;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (196 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > p.num_kb + 1 && p.num_tiles <= sms) stages = p.num_kb + 1 > 2 ? p.num_kb + 1 : 2;
   p.stages = stages;
@@ -723,7 +794,7 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
   const uint32_t mma_m = use2 ? 256u : 128u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
             ((uint32_t)(BN >> 3) << 17) | ((mma_m >> 4) << 24);
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 32 + 4 * kSlabBytes + 1024;
   const int kind = g.dtype == TNB200_F32 ? 1 : 0;
   static bool attr_set[4] = {false, false, false, false};
   const int ai = kind + (use2 ? 2 : 0);
