@@ -268,8 +268,8 @@ def main():
   sampler.join(timeout=2)
   result_value = [float(x) for x in np.atleast_1d(res.to_host().astype(np.float64))]
 
-  # ---- which kernel family carries the flops (one eager replica, names from the library)
-  kern_name, kern_share = dominant_kernel(be, dev, labels, path, work, nbatch)
+  # ---- per-kernel device times of one step (live, CUDA events) -> dominant kernel and its roofline
+  kstats = kernel_profile(be, dev, labels, path, work, nbatch, NB, esize)
 
   # ---- end-to-end timing (host buffers) ----------------------------------------------
   for _ in range(args.warmup):
@@ -303,8 +303,43 @@ def main():
       peak_src, peak_note = "derived", "tf32 = measured bf16 / 2 (no measured tf32 figure)"
     else:
       peak, peak_src, peak_note = 40.0, "nominal", "B200 FP64 nominal 40 TFLOP/s (no measured fp64 figure)"
-    # achieved: algorithmic flops of one step / device time of one step (all launches of the step are
-    # back to back in one CUDA graph, so this is flops / (sum of kernel durations + launch gaps))
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    if args.dtype == "bf16" and "bf16_tflops_sustained" in peaks:
+      # the dominant kernel is timed inside a long step: the sustained figure is its tensor roof
+      peak, peak_note = peaks["bf16_tflops_sustained"], "bf16 dense sustained (cuBLAS back to back), MEASURED_PEAKS.json"
+    # dominant kernel = the family with the largest share of the step's device time
+    ktot = sum(d["us"] for d in kstats.values())
+    kern_name = max(kstats, key=lambda k: kstats[k]["us"])
+    kd = kstats[kern_name]
+    k_tf = kd["flops"] / (kd["us"] * 1e-6) / 1e12
+    k_gbs = kd["bytes"] / (kd["us"] * 1e-6) / 1e9
+    t_tensor, t_hbm = kd["flops"] / (peak * 1e12), kd["bytes"] / (hbm_peak * 1e9)
+    if t_hbm >= t_tensor:
+      roof = {"bound": "hbm", "achieved": k_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k_gbs / hbm_peak}
+    else:
+      roof = {"bound": "tensor", "achieved": k_tf, "peak": peak, "unit": "TFLOP/s", "frac": k_tf / peak}
+    traffic = None
+    try:
+      tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+      if tr.get("kernel") == kern_name and tr.get("dtype") == args.dtype and tr.get("networks") == NB:
+        traffic = tr.get("dram_bytes_per_launch")
+    except Exception:  # pylint: disable=broad-except
+      pass
+    roof.update({
+        "traffic": traffic, "kernel": kern_name, "kernel_launches_per_step": kd["launches"],
+        "kernel_us_per_launch": kd["us"] / kd["launches"], "kernel_share_of_step_time": kd["us"] / ktot,
+        "algorithmic_mb_per_launch": kd["bytes"] / kd["launches"] / 1e6,
+        "algorithmic_gflop_per_launch": kd["flops"] / kd["launches"] / 1e9,
+        "kernel_tflops": k_tf, "kernel_gbs": k_gbs, "tensor_peak_tflops": peak, "hbm_peak_gbs": hbm_peak,
+        "peak_source": peak_src, "peak_note": peak_note,
+        "arithmetic_intensity_flop_per_byte": kd["flops"] / kd["bytes"], "ridge_flop_per_byte": peak * 1e3 / hbm_peak,
+        "note": "dominant kernel timed live with CUDA events around each of its launches (eager replay of the "
+                "step); algorithmic bytes = operands + result once, algorithmic flops = 2MNK; the binding roof "
+                "is the one with the larger minimum time",
+        "families": {k: {"launches": round(v["launches"], 2), "us": round(v["us"], 1),
+                         "tflops": round(v["flops"] / (v["us"] * 1e-6) / 1e12, 1),
+                         "gbs": round(v["bytes"] / (v["us"] * 1e-6) / 1e9, 1)} for k, v in kstats.items()},
+    })
     achieved = flops_step * args.steps / (ms * 1e-3) / 1e12
     value = world * NB * npair * args.steps / (ms * 1e-3)
     line = {
@@ -313,13 +348,10 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic", "config": workload_config(args, world),
         "step_tflops": world * achieved,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak, "traffic": None, "kernel": kern_name, "kernel_flop_share": kern_share,
-                     "peak_source": peak_src, "peak_note": peak_note,
-                     "launches_per_step": launches / args.steps,
-                     "algorithmic_gflop_per_step": flops_step / 1e9, "algorithmic_mb_per_step": bytes_step / 1e6,
-                     "note": "achieved = sum(2MNK over the step's pairwise contractions) / step device time "
-                             "(graph replay: kernel durations + inter-kernel gaps)"},
+        "step_hbm_gbs": world * bytes_step * args.steps / (ms * 1e-3) / 1e9,
+        "launches_per_step": launches / args.steps,
+        "algorithmic_gflop_per_step": flops_step / 1e9, "algorithmic_mb_per_step": bytes_step / 1e6,
+        "roofline": roof,
         "e2e": {"value": world * NB * npair * args.steps / (ms_e2e * 1e-3), "unit": "contractions/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": esize * NB,
                 "ms_per_step": ms_e2e / args.steps},
@@ -334,29 +366,43 @@ def main():
     dist.destroy_process_group()
 
 
-def dominant_kernel(be, dev, labels, path, work, nbatch):
-  """One eager replica of the step; the library reports which kernel family served each launch."""
+def kernel_profile(be, dev, labels, path, work, nbatch, nb, esize, reps=3):
+  """Per-kernel device time of one step, measured LIVE with CUDA events on the launching stream: the plan is
+  replayed eagerly `reps` times with an event pair around every pairwise contraction; the library reports which
+  kernel family served it.  Returns {family: {"launches", "us", "flops", "bytes"}} averaged per step
+  (bytes = algorithmic operand + result bytes of the contraction, each counted once)."""
   import torch
   from tensornetwork_b200 import drivers
   steps, _ = drivers.plan_path([t.shape for t in dev], labels, path, [], nbatch)
-  vals = list(dev)
-  tot = {}
-  wi = 0
-  for st in steps:
-    if st[0] in ("tensordot", "batched"):
-      if st[0] == "tensordot":
-        vals.append(be.tensordot(vals[st[1]], vals[st[2]], (st[3], st[4])))
+  stats = {}
+  for rep in range(reps + 1):
+    vals = list(dev)
+    evs = []
+    wi = 0
+    for st in steps:
+      if st[0] in ("tensordot", "batched"):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if st[0] == "tensordot":
+          vals.append(be.tensordot(vals[st[1]], vals[st[2]], (st[3], st[4])))
+        else:
+          vals.append(be._contract(vals[st[1]], vals[st[2]], list(st[3]), list(st[4]), list(st[5]), list(st[6])))
+        e1.record()
+        evs.append((be.lib.tnb200_last_kernel().decode(), work[wi], e0, e1))
+        wi += 1
       else:
-        vals.append(be._contract(vals[st[1]], vals[st[2]], list(st[3]), list(st[4]), list(st[5]), list(st[6])))
-      name = be.lib.tnb200_last_kernel().decode()
-      m, k, n = work[wi]
-      wi += 1
-      tot[name] = tot.get(name, 0.0) + 2.0 * m * k * n
-    else:
-      vals.append(be.transpose(vals[st[1]], st[2]))
-  torch.cuda.synchronize()
-  name = max(tot, key=lambda k: tot[k])
-  return name, tot[name] / sum(tot.values())
+        vals.append(be.transpose(vals[st[1]], st[2]))
+    torch.cuda.synchronize()
+    del vals
+    if rep == 0:
+      continue                                  # warm-up pass (allocator, descriptors)
+    for name, (m, k, n), e0, e1 in evs:
+      d = stats.setdefault(name, {"launches": 0, "us": 0.0, "flops": 0.0, "bytes": 0.0})
+      d["launches"] += 1.0 / reps
+      d["us"] += e0.elapsed_time(e1) * 1e3 / reps
+      d["flops"] += nb * 2.0 * m * k * n / reps
+      d["bytes"] += nb * float(m * k + k * n + m * n) * esize / reps
+  return stats
 
 
 def cpu_baseline(args):

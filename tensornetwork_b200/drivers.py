@@ -318,6 +318,33 @@ def greedy_path(labels, out_labels, size_dict, memory_limit=None):
                                            2**62 if memory_limit is None else memory_limit)]
 
 
+def _prefer_swapped(l1, l2, shared, sizes=None):
+  """True when tensordot(t2, t1) addresses memory better than tensordot(t1, t2): count operands whose
+  contracted axes are exactly the trailing axes (first operand, K-major rows) resp. the leading axes
+  (second operand, K x N row-major)."""
+  n = len(shared)
+  if n == 0:
+    return False
+  cs = set(shared)
+
+  def trailing(l):
+    return set(l[len(l) - n:]) == cs
+
+  def leading(l):
+    return set(l[:n]) == cs
+  keep = int(trailing(l1)) + int(leading(l2))
+  swap = int(trailing(l2)) + int(leading(l1))
+  if keep != swap or sizes is None:
+    return swap > keep
+  f1 = int(np.prod([sizes[0][i] for i, l in enumerate(l1) if l not in cs] or [1]))
+  f2 = int(np.prod([sizes[1][i] for i, l in enumerate(l2) if l not in cs] or [1]))
+  if leading(l1) and leading(l2):      # [k, m] . [k, n]: stream the long operand's free axes last
+    return f1 > f2
+  if trailing(l1) and trailing(l2):    # [m, k] . [n, k]: the long operand's rows first
+    return f1 < f2
+  return False
+
+
 def plan_path(shapes, labels, path, out_labels, nbatch=0):
   """contract_between (network_components.py:2048-2085) replayed symbolically along `path`.
 
@@ -333,6 +360,12 @@ def plan_path(shapes, labels, path, out_labels, nbatch=0):
     l1, l2 = labels[a], labels[b]
     s1, s2 = slots[a], slots[b]
     shared = [l for l in l1 if l in l2]
+    if _prefer_swapped(l1, l2, shared, (shp[s1][nbatch:], shp[s2][nbatch:])):
+      # the order of an INTERMEDIATE's axes is ours to choose (only the final result's order is
+      # observable, and the closing transpose restores it): put first the operand whose contracted
+      # axes trail, so that both operands and the output are plain row-major GEMM views
+      l1, l2, s1, s2 = l2, l1, s2, s1
+      shared = [l for l in l1 if l in l2]
     a1 = [l1.index(l) for l in shared]
     a2 = [l2.index(l) for l in shared]
     srt = sorted(range(len(a1)), key=lambda i: a1[i])

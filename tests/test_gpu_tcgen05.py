@@ -148,3 +148,72 @@ def test_swap_ab_tiny_m(dtype):
   out = be._contract(Ab, Bb, [1], [2], [0], [0])
   ref = np.einsum("bkpq,bxkcdefghi->bpqxcdefghi", ab, bb)
   assert rel_err(out.to_host(), ref) < TOLS[dtype]
+
+
+# ------------------------------------------------------------------------------------------------
+# thin contractions (tensordot_thin.cu): small matrix x long tensor, the ramp-up steps of the cfg-2 path
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16", "float32"])
+@pytest.mark.parametrize("kp", [(2, 2), (4, 4), (8, 8), (4, 8), (8, 2), (3, 5)])
+def test_thin_simt_both_layouts(dtype, kp):
+  be = get_backend()
+  rng = np.random.default_rng(31)
+  k, p = kp
+  nb, L = 3, 32768
+  tol = TOLS[dtype] if dtype != "float32" else 2e-5
+  # mode A: S[b, p1, 2, k] . X[b, k, (2, 2, L/4)] -> C[b, p1, 2, 2, 2, L/4]  (many-leg operands, merged by the planner)
+  if p % 2 == 0:
+    S, s = _mk(be, rng, (nb, p // 2, 2, k), dtype)
+    X, x = _mk(be, rng, (nb, k, 2, 2, L // 4), dtype)
+    out = be._contract(S, X, [3], [1], [0], [0])
+    assert be.lib.tnb200_last_kernel().decode() == "thin_simt_a"
+    e = rel_err(out.to_host(), np.einsum("bpqk,bkxyl->bpqxyl", s, x))
+    assert e < tol, (dtype, kp, "A", e)
+  else:
+    S, s = _mk(be, rng, (nb, p, k), dtype)
+    X, x = _mk(be, rng, (nb, k, L), dtype)
+    out = be._contract(S, X, [2], [1], [0], [0])
+    assert be.lib.tnb200_last_kernel().decode() == "thin_simt_a"
+    assert rel_err(out.to_host(), np.einsum("bpk,bkl->bpl", s, x)) < tol, (dtype, kp, "A")
+  # mode D: X[b, L, k] . S[b, k, p] -> C[b, L, p]   (power-of-two K, P only; others take the generic paths)
+  X, x = _mk(be, rng, (nb, L // 2, 2, k), dtype)
+  S, s = _mk(be, rng, (nb, k, p), dtype)
+  out = be._contract(X, S, [3], [1], [0], [0])
+  kern = be.lib.tnb200_last_kernel().decode()
+  if k in (2, 4, 8) and p in (2, 4, 8):
+    assert kern == "thin_simt_d", kern
+  e = rel_err(out.to_host(), np.einsum("bxyk,bkp->bxyp", x, s))
+  assert e < tol, (dtype, kp, "D", kern, e)
+
+
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+@pytest.mark.parametrize("kp", [(16, 16), (32, 32), (64, 64), (16, 64), (64, 16), (32, 64), (64, 32), (16, 32), (32, 16)])
+def test_thin_mma_both_layouts(dtype, kp):
+  be = get_backend()
+  rng = np.random.default_rng(32)
+  k, p = kp
+  nb, L = 5, 16384
+  # mode A with a two-leg S (site tensor (p/2, 2, k)) and batch
+  S, s = _mk(be, rng, (nb, p // 2, 2, k), dtype)
+  X, x = _mk(be, rng, (nb, k, 2, L // 2), dtype)
+  out = be._contract(S, X, [3], [1], [0], [0])
+  assert be.lib.tnb200_last_kernel().decode() == "thin_mma_a"
+  e = rel_err(out.to_host(), np.einsum("bpqk,bkxl->bpqxl", s, x))
+  assert e < TOLS[dtype], (dtype, kp, "A", e)
+  # mode D with a two-leg S (site tensor (k, 2, p/2))
+  X, x = _mk(be, rng, (nb, L, k), dtype)
+  S, s = _mk(be, rng, (nb, k, 2, p // 2), dtype)
+  out = be._contract(X, S, [2], [1], [0], [0])
+  assert be.lib.tnb200_last_kernel().decode() == "thin_mma_d"
+  e = rel_err(out.to_host(), np.einsum("blk,bkqp->blqp", x, s))
+  assert e < TOLS[dtype], (dtype, kp, "D", e)
+
+
+def test_thin_mma_masked_rows_and_unbatched():
+  """P not a multiple of 16 (mode A masks rows), no batch axis, transposed S view."""
+  be = get_backend()
+  rng = np.random.default_rng(33)
+  S, s = _mk(be, rng, (32, 24), "bfloat16")          # stored [k][p]; used as S^T
+  X, x = _mk(be, rng, (32, 131072), "bfloat16")
+  out = be.tensordot(be.transpose(S), X, 1)
+  assert be.lib.tnb200_last_kernel().decode() == "thin_mma_a"
+  assert rel_err(out.to_host(), s.T @ x) < TOLS["bfloat16"]
