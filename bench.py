@@ -174,12 +174,19 @@ def main():
   ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
   ap.add_argument("--cpu-baseline-steps", type=int, default=2)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg1", "flagship", "cfg3", "cfg4", "cfg5", "tree32"],
+                  help="cfg2 (default) is the headline line of the driver contract; the others are the remaining "
+                       "SURVEY 8(d) configurations, single GPU, same JSON keys")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "cuda_b200" else max(args.warmup, 1)
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local = int(os.environ.get("LOCAL_RANK", "0"))
 
+  if args.config != "cfg2":
+    if rank == 0:
+      run_config(args)
+    return
   if args.impl == "reference":
     run_reference(args, rank, world)
     return
@@ -422,6 +429,256 @@ def cpu_baseline(args):
   dt = time.perf_counter() - t0
   return {"value": (len(tensors) - 1) * n / dt, "unit": "contractions/s", "cores": os.cpu_count(), "kind": "port",
           "sample": "%d full networks (127 pairwise each) in numpy %s, all host threads" % (n, np.dtype(np_dtype).name)}
+
+
+# ------------------------------------------------------------------ the other SURVEY 8(d) configurations
+def _peaks():
+  try:
+    return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+  except Exception:  # pylint: disable=broad-except
+    return {}
+
+
+def _time_gpu(fn, steps, warmup, flush=None):
+  """CUDA-event time of `steps` calls of fn() (ms per call); `flush()` (untimed part excluded by its own
+  events) is called between iterations when the inputs fit in L2."""
+  import torch
+  for _ in range(max(warmup, 3)):
+    fn()
+  torch.cuda.synchronize()
+  tot = 0.0
+  for _ in range(steps):
+    if flush is not None:
+      flush()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    tot += e0.elapsed_time(e1)
+  return tot / steps
+
+
+def _time_cpu(fn, reps, warm=1):
+  for _ in range(warm):
+    fn()
+  ts = []
+  for _ in range(reps):
+    t0 = time.perf_counter()
+    fn()
+    ts.append(time.perf_counter() - t0)
+  return float(np.median(ts))
+
+
+def run_config(args):
+  """One JSON line per configuration, same keys as the headline line where they apply (N = 1)."""
+  import torch
+  torch.cuda.set_device(0)
+  import tensornetwork_b200 as tb
+  from tensornetwork_b200 import drivers
+  from oracle import np_backend as nb, np_network as nn          # cpu_baseline leg only
+  be = tb.get_backend()
+  lib = be.lib
+  peaks = _peaks()
+  hbm_peak = peaks.get("hbm_gbs", 6650.0)
+  np_dt = {"bf16": np.float32, "f32": np.float32, "f64": np.float64}[args.dtype]
+  be_dt = {"bf16": "bfloat16", "f32": np.float32, "f64": np.float64}[args.dtype]
+  esize = {"bf16": 2, "f32": 4, "f64": 8}[args.dtype]
+  tensor_peak = {"bf16": peaks.get("bf16_tflops", 1590.0), "f32": peaks.get("bf16_tflops", 1590.0) / 2.0, "f64": 40.0}[args.dtype]
+  flushbuf = torch.empty(256 << 20, dtype=torch.uint8, device=be.device)
+  flush = lambda: flushbuf.zero_()                       # 256 MB write > 126 MB L2
+  sampler = ClockSampler(0)
+  sampler.start()
+  cfg = args.config
+  steps = args.steps
+  line = {"n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": args.dtype, "data": "synthetic"}
+  l0 = lib.tnb200_launch_count()
+
+  if cfg == "cfg1":
+    # SURVEY 8(d) cfg 1: ncon of two 10x10 fp64 matrices — pure call-overhead number
+    rng = np.random.default_rng(1)
+    a, b = rng.standard_normal((10, 10)), rng.standard_normal((10, 10))
+    A, B = be.convert_to_tensor(a), be.convert_to_tensor(b)
+    net = [(-1, 1), (1, -2)]
+    ms = _time_gpu(lambda: drivers.ncon([A, B], net, backend=be), steps, args.warmup)
+    cpu = _time_cpu(lambda: nn.ncon([a, b], net), 200, 20)
+    ok = np.allclose(drivers.ncon([A, B], net, backend=be).to_host(), nn.ncon([a, b], net), rtol=1e-12)
+    line.update({"metric": "pairwise contractions/s", "value": 1e3 / ms, "unit": "contractions/s", "ms_per_step": ms, "dtype": "f64",
+                 "config": {"workload": "cfg1: ncon([a,b],[(-1,1),(1,-2)]) on 10x10 fp64 (latency-bound, host plan + one launch)"},
+                 "roofline": None, "parity_ok": bool(ok),
+                 "cpu_baseline": {"value": 1.0 / cpu, "unit": "contractions/s", "cores": 1, "kind": "port",
+                                  "sample": "200 calls of the numpy ncon restatement, median"}})
+  elif cfg == "flagship":
+    # SURVEY 8(d) flagship: A,B (512,2,512), tensordot over the shared bond -> (512,2,2,512); M=1024,K=512,N=1024
+    rng = np.random.default_rng(2)
+    a = (rng.standard_normal((512, 2, 512)) / np.sqrt(512)).astype(np_dt)
+    b = (rng.standard_normal((512, 2, 512)) / np.sqrt(512)).astype(np_dt)
+    A, B = be.astype(be.convert_to_tensor(a), be_dt), be.astype(be.convert_to_tensor(b), be_dt)
+    ms = _time_gpu(lambda: be.tensordot(A, B, [[2], [0]]), steps, args.warmup, flush)
+    kern = lib.tnb200_last_kernel().decode()
+    flops, byts = 2.0 * 1024 * 512 * 1024, (1024 * 512 * 2 + 1024 * 1024) * esize
+    out = be.tensordot(A, B, [[2], [0]]).to_host().astype(np.float64)
+    ref = np.tensordot(A.to_host().astype(np.float64), B.to_host().astype(np.float64), [[2], [0]])
+    err = float(np.linalg.norm(out - ref) / np.linalg.norm(ref))
+    cpu = _time_cpu(lambda: nb.tensordot(a, b, [[2], [0]]), 10, 3)
+    tf, gbs = flops / ms / 1e9, byts / ms / 1e6
+    t_t, t_h = flops / (tensor_peak * 1e12), byts / (hbm_peak * 1e9)
+    line.update({"metric": "pairwise contractions/s", "value": 1e3 / ms, "unit": "contractions/s", "ms_per_step": ms,
+                 "config": {"workload": "flagship: tensordot(A(512,2,512), B(512,2,512), [[2],[0]]), one unbatched call, L2 flushed "
+                                        "(256 MB write) between timed calls"},
+                 "roofline": {"bound": "tensor" if t_t >= t_h else "hbm", "achieved": tf if t_t >= t_h else gbs,
+                              "peak": tensor_peak if t_t >= t_h else hbm_peak, "unit": "TFLOP/s" if t_t >= t_h else "GB/s",
+                              "frac": (tf / tensor_peak) if t_t >= t_h else (gbs / hbm_peak), "traffic": None, "kernel": kern,
+                              "kernel_tflops": tf, "kernel_gbs": gbs,
+                              "note": "single 1.07 GFLOP call on 148 SMs: 32 output tiles of 128x256 -> at most 32 SMs busy; "
+                                      "the batched form of the same shape is what the cfg2 line measures"},
+                 "rel_err_vs_fp64": err,
+                 "cpu_baseline": {"value": 1.0 / cpu, "unit": "contractions/s", "cores": os.cpu_count(), "kind": "port",
+                                  "sample": "numpy tensordot %s, median of 10" % np.dtype(np_dt).name,
+                                  "gflops": flops / cpu / 1e9}})
+  elif cfg == "cfg3":
+    # SURVEY 8(d) cfg 3: split_node_full_svd of (64,64,64,64) with max_singular_values=256
+    rng = np.random.default_rng(4)
+    m = (rng.standard_normal((64, 64, 64, 64)) / 64.0).astype(np.float64 if args.dtype == "f64" else np.float32)
+    M = be.convert_to_tensor(m)
+    steps = min(steps, 3)
+    res = {}
+    def f():
+      res["o"] = drivers.split_full_svd(M, [0, 1], [2, 3], max_singular_values=256, backend=be)
+    ms = _time_gpu(f, steps, 1)
+    u, s, vh, trun = res["o"]
+    t0 = time.perf_counter()
+    ru, rs, rvh, rtr = nb.svd(m, 2, 256, None, False)
+    cpu = time.perf_counter() - t0
+    sv = np.diag(s.to_host())
+    err_s = float(np.abs(sv - rs).max() / rs[0])
+    shapes_ok = u.shape == ru.shape and vh.shape == rvh.shape and tuple(trun.shape) == rtr.shape
+    flops = 21.0 * 4096.0**3
+    line.update({"metric": "split_node_full_svd/s", "value": 1e3 / ms, "unit": "splits/s", "ms_per_step": ms, "steps": steps,
+                 "dtype": "f64" if args.dtype == "f64" else "f32 storage, f64 Jacobi iteration",
+                 "config": {"workload": "cfg3: split_node_full_svd of a (64,64,64,64) tensor (4096x4096), max_singular_values=256"},
+                 "roofline": {"bound": "fp64 pipe", "achieved": flops / ms / 1e9, "peak": 40.0, "unit": "TFLOP/s",
+                              "frac": flops / ms / 1e9 / 40.0, "traffic": None, "kernel": "svd_jacobi (gram/eig/update)",
+                              "note": "flops by the 21 n^3 Golub-Reinsch convention (SURVEY 8d) irrespective of Jacobi sweeps; "
+                                      "nominal 40 TFLOP/s fp64"},
+                 "parity": {"singular_values_max_rel_err": err_s, "shapes_equal": bool(shapes_ok), "kept": int(sv.shape[0])},
+                 "cpu_baseline": {"value": 1.0 / cpu, "unit": "splits/s", "cores": os.cpu_count(), "kind": "port",
+                                  "sample": "1 call of the numpy (LAPACK gesdd) restatement", "seconds": cpu}})
+  elif cfg == "cfg4":
+    # SURVEY 8(d) cfg 4: U(1) block-sparse tensordot(A, conj(A), ([2,3],[2,3])), 4 legs of dim 32 (and the x2 scale-up)
+    from tensornetwork_b200 import blocksparse as bs
+    from oracle import np_blocksparse as nbs
+    outs = []
+    for dim in (32, 64):
+      rng = np.random.RandomState(5)
+      charges = [rng.randint(-8, 9, dim).astype(np.int64) for _ in range(4)]
+      flows = [False, False, True, True]
+      legs = [bs.Index(c, f) for c, f in zip(charges, flows)]
+      A = bs.BlockSparseTensor.randn(legs, dtype=np.float64, seed=5, backend=be)
+      Ac = A.conj()
+      t0 = time.perf_counter()
+      C = bs.tensordot(A, Ac, ([2, 3], [2, 3]))
+      torch.cuda.synchronize()
+      first = time.perf_counter() - t0
+      ms = _time_gpu(lambda: bs.tensordot(A, Ac, ([2, 3], [2, 3])), steps, args.warmup, flush)
+      a_host = A.data.to_host()
+      t0 = time.perf_counter()
+      cref, _, _ = nbs.tensordot_trailing(a_host, charges, flows, np.conj(a_host), charges, [not f for f in flows], 2)
+      cpu = time.perf_counter() - t0
+      cpu = min(cpu, _time_cpu(lambda: nbs.tensordot_trailing(a_host, charges, flows, np.conj(a_host), charges,
+                                                              [not f for f in flows], 2), 3, 0))
+      err = float(np.linalg.norm(C.data.to_host() - cref) / np.linalg.norm(cref))
+      nnz = a_host.shape[0]
+      byts = (2 * nnz + cref.shape[0]) * 8 * 2.0          # payload + the int64 gather/scatter maps
+      outs.append({"leg_dim": dim, "nnz_a": int(nnz), "nnz_c": int(cref.shape[0]), "mflop": C.last_flops / 1e6,
+                   "gpu_ms_steady": ms, "gpu_ms_first_call_with_host_maps": first * 1e3, "gbs": byts / ms / 1e6,
+                   "gflops": C.last_flops / ms / 1e6, "cpu_ms": cpu * 1e3, "rel_err": err})
+    o = outs[0]
+    line.update({"metric": "pairwise contractions/s", "value": 1e3 / o["gpu_ms_steady"], "unit": "contractions/s",
+                 "ms_per_step": o["gpu_ms_steady"], "dtype": "f64",
+                 "config": {"workload": "cfg4: U(1) block-sparse tensordot(A, conj(A), ([2,3],[2,3])), 4 legs x dim 32, charges in [-8,8] "
+                                        "(one grouped gather-GEMM-scatter launch over all sectors; maps cached on device)"},
+                 "roofline": {"bound": "hbm", "achieved": o["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": o["gbs"] / hbm_peak,
+                              "traffic": None, "kernel": "blocksparse_grouped",
+                              "note": "3.8 MFLOP / 1 MB problem: launch-latency bound; the dim-64 scale-up is in `sizes`"},
+                 "sizes": outs,
+                 "cpu_baseline": {"value": 1e3 / o["cpu_ms"], "unit": "contractions/s", "cores": os.cpu_count(), "kind": "port",
+                                  "sample": "numpy restatement incl. block-map construction per call (the reference recomputes maps "
+                                            "unless its cache is enabled), best of 4"}})
+  elif cfg == "cfg5":
+    # SURVEY 8(d) cfg 5: two-site DMRG of the XXZ chain at saturated bond dimension D (time per site update)
+    from tensornetwork_b200 import dmrg
+    from oracle import np_ops
+    D = int(os.environ.get("TNB200_CFG5_D", "1024"))
+    N = 2 * int(np.ceil(np.log2(D))) + 12
+    rng = np.random.default_rng(6)
+    dims = [min(D, 2**min(i, N - i)) for i in range(N + 1)]
+    mps = []
+    for i in range(N):                                    # right-orthonormal random MPS (centre at site 0)
+      q, _ = np.linalg.qr(rng.standard_normal((2 * dims[i + 1], dims[i])))
+      mps.append(np.ascontiguousarray(q.T.reshape(dims[i], dims[i + 1], 2).transpose(0, 2, 1)))
+    mpo = dmrg.xxz_mpo(np.ones(N - 1), np.ones(N - 1), np.zeros(N), np.float64)
+    lo = int(np.ceil(np.log2(D)))                         # first bond with D_l = D
+    nsite = max(2, min(steps, N - 2 * lo - 2))
+
+    def sweep(ops, sync, count):
+      eng = dmrg.TwoSiteDMRG(ops, mps, mpo, center_position=0)
+      eng.compute_right_envs()
+      times, e = [], None
+      while eng.center < lo + count:
+        sync()
+        t0 = time.perf_counter()
+        e = eng.optimize_two_sites(D, "right", num_krylov_vecs=10, tol=1e-5, delta=1e-6, ndiag=10)
+        sync()
+        if eng.center > lo:
+          times.append(time.perf_counter() - t0)
+      return times, float(np.real(e.to_host() if hasattr(e, "to_host") else e)), eng.num_matvecs
+    tg, eg, mv = sweep(dmrg.BackendOps(be), torch.cuda.synchronize, nsite)
+    ncpu = 1 if D >= 512 else 2
+    tc, ec, _ = sweep(np_ops.NumpyOps(), lambda: None, ncpu) if not args.no_cpu_baseline else ([float("nan")], float("nan"), 0)
+    ms = float(np.median(tg)) * 1e3
+    flops_mv = 2.0 * (D * 5) * D * (2 * 2 * D) * 2 + 2.0 * (D * 2 * D * 2) * (5 * 2) * (5 * 2) * 2   # 4 tensordots per matvec
+    line.update({"metric": "two-site DMRG site updates/s", "value": 1e3 / ms, "unit": "site-updates/s", "ms_per_step": ms,
+                 "steps": len(tg), "dtype": "f64",
+                 "config": {"workload": "cfg5: XXZ (Jz=Jxy=1, Bz=0) two-site DMRG, fp64, D=%d saturated, N=%d sites (interior site cost is "
+                                        "independent of N), <=10 Krylov vectors, SVD truncation to D, wall clock incl. host driver" % (D, N)},
+                 "roofline": {"bound": "fp64 pipe", "achieved": None, "peak": 40.0, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                              "kernel": "gemm_dmma_f64 + svd_jacobi", "approx_gflop_per_matvec": flops_mv / 1e9},
+                 "site_update_seconds": tg, "energy_after_last_update": eg,
+                 "cpu_baseline": {"value": 1.0 / float(np.median(tc)), "unit": "site-updates/s", "cores": os.cpu_count(), "kind": "port",
+                                  "sample": "%d saturated site update(s) of the same driver on the numpy oracle" % ncpu,
+                                  "energy_after_last_update": ec, "site_update_seconds": tc}})
+  elif cfg == "tree32":
+    # SURVEY 8(d) 32-node network: <T|T> of a random 16-node tree tensor network, chi=128, d=2
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from multigpu_check import tree_network
+    tensors, labels, sizes = tree_network(chi=128)
+    host = [t.astype(np_dt) for t in tensors]
+    dev = [be.astype(be.convert_to_tensor(t), be_dt) for t in host]
+    path = drivers.greedy_path(labels, [], sizes)
+    flops = float(sum(2.0 * m * k * n for m, k, n in nn.network_flops(labels, path, sizes)))
+    net = drivers.CompiledNetwork(be, [t.shape for t in dev], be_dt, labels, [], path=path)
+    net.load(dev)
+    ms = _time_gpu(lambda: net(), steps, args.warmup, flush)
+    out = float(net().to_host().astype(np.float64))
+    ref = float(nn.contract_path([h.astype(np.float64) for h in host], labels, path, []))
+    cpu = _time_cpu(lambda: nn.contract_path(host, labels, path, []), 3, 1)
+    npair = len(path)
+    line.update({"metric": "pairwise contractions/s", "value": npair * 1e3 / ms, "unit": "contractions/s", "ms_per_step": ms,
+                 "config": {"workload": "tree32: <T|T> of a random 16-node tree tensor network (32 tensors, chi=128, d=2), greedy path, "
+                                        "CUDA-graph replay, L2 flushed between replays"},
+                 "roofline": {"bound": "tensor", "achieved": flops / ms / 1e9, "peak": tensor_peak, "unit": "TFLOP/s",
+                              "frac": flops / ms / 1e9 / tensor_peak, "traffic": None, "kernel": "mixed (whole network)",
+                              "algorithmic_gflop_per_step": flops / 1e9},
+                 "result": out, "reference_result_fp64": ref, "rel_err": abs(out - ref) / abs(ref),
+                 "cpu_baseline": {"value": npair / cpu, "unit": "contractions/s", "cores": os.cpu_count(), "kind": "port",
+                                  "sample": "3 full networks in numpy %s, median" % np.dtype(np_dt).name}})
+  line["gpu_launches"] = int(lib.tnb200_launch_count() - l0)
+  sampler.stop_flag = True
+  sampler.join(timeout=2)
+  line["clocks"] = sampler.summary()
+  print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -114,7 +114,12 @@ class BlockSparseTensor:
   # ------------------------------------------------------------------ constructors
   @classmethod
   def _nnz(cls, indices):
-    return int(_fused_allowed(indices).shape[0])
+    key = ("nnz", tuple(ix.key() for ix in indices))
+    hit = _MAP_CACHE.get(key)
+    if hit is None:
+      hit = int(_fused_allowed(indices).shape[0])
+      _MAP_CACHE[key] = hit
+    return hit
 
   @classmethod
   def zeros(cls, indices, dtype=np.float64, backend=None):
@@ -242,6 +247,25 @@ def tensordot(a, b, axes):
   free_a = [i for i in range(a.ndim) if i not in axes_a]
   free_b = [i for i in range(b.ndim) if i not in axes_b]
   out_indices = [a.indices[a.order[i]] for i in free_a] + [b.indices[b.order[i]] for i in free_b]
+  # everything below up to the launch depends only on the charge structure: one cached plan per
+  # (legs, orders, axes), so a repeated contraction costs one kernel launch and no host index work
+  pkey = ("plan", tuple(ix.key() for ix in a.indices), tuple(a.order), tuple(ix.key() for ix in b.indices),
+          tuple(b.order), tuple(axes_a), tuple(axes_b), a.data.code)
+  plan = _MAP_CACHE.get(pkey)
+  if plan is not None:
+    nnz_c, dev = plan
+    c_data = be.zeros((nnz_c,), a.data.dtype)
+    if dev is None:
+      return BlockSparseTensor(c_data, out_indices, backend=be)
+    rc = be.lib.tnb200_blocksparse_tensordot(
+        a.data.t.data_ptr(), b.data.t.data_ptr(), c_data.t.data_ptr(), a.data.code, dev["nsect"],
+        dev["dims"].data_ptr(), dev["am"].data_ptr(), dev["ao"].data_ptr(), dev["bm"].data_ptr(),
+        dev["bo"].data_ptr(), dev["cm"].data_ptr(), dev["co"].data_ptr(), dev["max_m"], dev["max_n"], 0,
+        be._stream())  # pylint: disable=protected-access
+    L.check(rc)
+    out = BlockSparseTensor(c_data, out_indices, backend=be)
+    out.last_flops = dev["flops"]
+    return out
   # matrix views: A = (free_a | axes_a), B = (axes_b | free_b), C = (free_a | free_b)
   order_a = [a.order[i] for i in free_a] + [a.order[i] for i in axes_a]
   order_b = [b.order[i] for i in axes_b] + [b.order[i] for i in free_b]
@@ -265,6 +289,7 @@ def tensordot(a, b, axes):
         raise RuntimeError("block-sparse sector bookkeeping mismatch (internal error)")
       sect.append((i, j, k, m_, k_, n_))
   if not sect or nnz_c == 0:
+    _MAP_CACHE[pkey] = (nnz_c, None)
     return BlockSparseTensor(c_data, out_indices, backend=be)
   key = ("td", id(ma), id(mb), id(mc), tuple(s[:3] for s in sect))
   dev = _MAP_CACHE.get(key)
@@ -285,6 +310,7 @@ def tensordot(a, b, axes):
                max_m=int(dims[:, 0].max()), max_n=int(dims[:, 2].max()), nsect=len(sect),
                keep=(ma, mb, mc), flops=float(2 * (dims[:, 0] * dims[:, 1] * dims[:, 2]).sum()))
     _MAP_CACHE[key] = dev
+  _MAP_CACHE[pkey] = (nnz_c, dev)
   rc = be.lib.tnb200_blocksparse_tensordot(
       a.data.t.data_ptr(), b.data.t.data_ptr(), c_data.t.data_ptr(), a.data.code, dev["nsect"],
       dev["dims"].data_ptr(), dev["am"].data_ptr(), dev["ao"].data_ptr(), dev["bm"].data_ptr(),

@@ -153,6 +153,66 @@ __global__ void __launch_bounds__(256) skinny_dot_kernel(const __grid_constant__
     }
   }
 }
+// Fast path of the same reduction when both operands are packed [K][M] / [K][N] with M == N == MN: every
+// thread streams 16-byte vectors (16/sizeof(T)/MN whole k-rows each) of A and B, four vector pairs in flight.
+template <typename T, typename Acc, int MN>
+__global__ void __launch_bounds__(256) skinny_dot_vec_kernel(const __grid_constant__ DotParams<T> p) {
+  constexpr int VE = 16 / (int)sizeof(T);
+  constexpr int R = VE / MN;                     // k-rows per vector
+  __shared__ Acc red[8][MN * MN];
+  const int64_t bb = blockIdx.x;
+  int64_t offAb, offBb, offCb;
+  mode_offsets3(p.mB, bb, offAb, offBb, offCb);
+  const T* Ap = p.A + offAb;
+  const T* Bp = p.B + offBb;
+  struct alignas(16) Pack { T v[VE]; };
+  Acc acc[MN][MN];
+#pragma unroll
+  for (int m = 0; m < MN; ++m)
+#pragma unroll
+    for (int n = 0; n < MN; ++n) acc[m][n] = acc_zero((Acc*)nullptr);
+  const int64_t nvec = p.K * MN / VE;
+  const int64_t v0 = (int64_t)blockIdx.y * p.kchunk;             // kchunk counts vectors here
+  const int64_t v1 = v0 + p.kchunk < nvec ? v0 + p.kchunk : nvec;
+  constexpr int U = 4;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += 256 * U) {
+    Pack a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (v + u * 256 < v1) {
+        *reinterpret_cast<uint4*>(&a[u]) = __ldg(reinterpret_cast<const uint4*>(Ap + (v + u * 256) * VE));
+        *reinterpret_cast<uint4*>(&b[u]) = __ldg(reinterpret_cast<const uint4*>(Bp + (v + u * 256) * VE));
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (v + u * 256 < v1) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int m = 0; m < MN; ++m) {
+            const Acc av = to_acc(a[u].v[r * MN + m]);
+#pragma unroll
+            for (int n = 0; n < MN; ++n) fma_acc(acc[m][n], av, to_acc(b[u].v[r * MN + n]));
+          }
+      }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int m = 0; m < MN; ++m)
+#pragma unroll
+    for (int n = 0; n < MN; ++n) {
+      Acc x = acc[m][n];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) red[warp][m * MN + n] = x;
+    }
+  __syncthreads();
+  if (threadIdx.x < MN * MN) {
+    Acc x = acc_zero((Acc*)nullptr);
+    for (int w = 0; w < 8; ++w) x += red[w][threadIdx.x];
+    atomicAdd((Acc*)p.ws + bb * MN * MN + threadIdx.x, x);
+  }
+}
+
 template <typename T, typename Acc>
 __global__ void skinny_dot_finalize(const __grid_constant__ DotParams<T> p) {
   const int64_t total = p.batch * p.M * p.N;
@@ -209,6 +269,38 @@ static int run_dot(const void* A, const void* B, void* C, const ModeList& mB, co
   if (!to_dev(mB, p.mB) || !to_dev(mM, p.mM) || !to_dev(mN, p.mN) || !to_dev(mK, p.mK)) return TNB200_ERR_UNSUPPORTED;
   p.K = mK.total(); p.batch = mB.total(); p.M = (int)mM.total(); p.N = (int)mN.total();
   if (p.batch >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
+  // packed fast path: A = [K][M], B = [K][N], M == N in {1, 2, 4}, 16-byte aligned rows of vectors
+  {
+    constexpr int VE = 16 / (int)sizeof(T);
+    const bool packed = mK.n == 1 && p.M == p.N && (p.M == 1 || p.M == 2 || p.M == 4) && p.M <= VE &&
+                        mK.s0[0] == p.M && mK.s1[0] == p.N &&
+                        (p.M == 1 || (mM.n == 1 && mN.n == 1 && mM.s0[0] == 1 && mN.s0[0] == 1)) &&
+                        (p.K * p.M) % VE == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && p.batch <= 65535;
+    bool al = packed;
+    for (int i = 0; i < mB.n && al; ++i) al = mB.s0[i] % VE == 0 && mB.s1[i] % VE == 0;
+    if (al) {
+      const int64_t nvec = p.K * p.M / VE;
+      int64_t want = ((int64_t)num_sms() * 8 + p.batch - 1) / p.batch;
+      const int64_t maxsp = (nvec + 1023) / 1024;
+      int64_t sp = want < maxsp ? want : maxsp; if (sp < 1) sp = 1; if (sp > 65535) sp = 65535;
+      p.kchunk = (nvec + sp - 1) / sp;
+      sp = (nvec + p.kchunk - 1) / p.kchunk;
+      const size_t bytes = sizeof(Acc) * (size_t)(p.batch * p.M * p.N);
+      int rc = ws_alloc(&p.ws, bytes, st);
+      if (rc) return rc;
+      TNB_CHECK_CUDA(cudaMemsetAsync(p.ws, 0, bytes, st));
+      dim3 grid((unsigned)p.batch, (unsigned)sp);
+      if (p.M == 1) skinny_dot_vec_kernel<T, Acc, 1><<<grid, 256, 0, st>>>(p);
+      else if (p.M == 2) skinny_dot_vec_kernel<T, Acc, 2><<<grid, 256, 0, st>>>(p);
+      else skinny_dot_vec_kernel<T, Acc, 4><<<grid, 256, 0, st>>>(p);
+      const int64_t tot = p.batch * p.M * p.N;
+      skinny_dot_finalize<T, Acc><<<(unsigned)((tot + 255) / 256 < 1024 ? (tot + 255) / 256 : 1024), 256, 0, st>>>(p);
+      TNB_LAUNCH_CHECK();
+      count_launch(2);
+      set_kernel_name("skinny_dot");
+      return ws_free(p.ws, st);
+    }
+  }
   // inner block = trailing K modes whose product stays <= DOT_IB (single-mode K: split it evenly)
   int64_t inner = 1;
   {

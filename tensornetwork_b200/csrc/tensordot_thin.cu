@@ -35,17 +35,20 @@ template <typename T> struct Vec16 { static constexpr int N = 16 / (int)sizeof(T
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // ------------------------------------------------------------------------------------------ SIMT, mode A
-template <typename T, typename Acc>
+// KK / PP: compile-time upper bounds (2, 4, 8) of the runtime K and P, so that small problems keep few
+// registers (high occupancy = more bytes in flight); U units of 16 bytes per thread are loaded before use.
+template <typename T, typename Acc, int KK, int PP>
 __global__ void __launch_bounds__(256) thin_simt_a_kernel(const __grid_constant__ ThinParams p) {
   constexpr int VE = Vec16<T>::N;
-  __shared__ __align__(16) Acc sS[8][8];      // [k][p], zero padded
-  __shared__ long long cOff[8];
+  constexpr int U = (KK * PP <= 16) ? 2 : 1;
+  __shared__ __align__(16) Acc sS[KK][PP];    // [k][p], zero padded
+  __shared__ long long cOff[PP];
   const int64_t bb = blockIdx.y;
   const T* Xb = (const T*)p.X + bb * p.bX;
   const T* Sb = (const T*)p.S + bb * p.bS;
   T* Cb = (T*)p.C + bb * p.bC;
-  if (threadIdx.x < 64) {
-    const int k = threadIdx.x >> 3, pp = threadIdx.x & 7;
+  if (threadIdx.x < KK * PP) {
+    const int k = threadIdx.x / PP, pp = threadIdx.x % PP;
     Acc v = acc_zero((Acc*)nullptr);
     if (pp < p.P) {
       int64_t os, oc;
@@ -56,39 +59,53 @@ __global__ void __launch_bounds__(256) thin_simt_a_kernel(const __grid_constant_
     sS[k][pp] = v;
   }
   __syncthreads();
+  Acc w[KK][PP];
+#pragma unroll
+  for (int k = 0; k < KK; ++k)
+#pragma unroll
+    for (int i = 0; i < PP; ++i) w[k][i] = sS[k][i];
+  long long co[PP];
+#pragma unroll
+  for (int i = 0; i < PP; ++i) co[i] = i < p.P ? cOff[i] : 0;
   struct alignas(16) Pack { T v[VE]; };
   const int64_t nunits = p.L / VE;
-  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < nunits; u += (int64_t)gridDim.x * blockDim.x) {
-    const T* xp = Xb + u * VE;
-    Pack x[8];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t u0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u0 < nunits; u0 += stride * U) {
+    Pack x[U][KK];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (k < p.K) *reinterpret_cast<uint4*>(&x[k]) = ldg16(xp + k * p.sXk);
-    Acc acc[8][VE];
+    for (int j = 0; j < U; ++j)
+      if (u0 + j * stride < nunits) {
+        const T* xp = Xb + (u0 + j * stride) * VE;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int v = 0; v < VE; ++v) acc[i][v] = acc_zero((Acc*)nullptr);
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (k < p.K) {
-        Acc w[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = sS[k][i];
-#pragma unroll
-        for (int v = 0; v < VE; ++v) {
-          const Acc xv = to_acc(x[k].v[v]);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) fma_acc(acc[i][v], w[i], xv);
-        }
+        for (int k = 0; k < KK; ++k)
+          if (k < p.K) *reinterpret_cast<uint4*>(&x[j][k]) = ldg16(xp + k * p.sXk);
       }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < p.P) {
-        Pack o;
+    for (int j = 0; j < U; ++j)
+      if (u0 + j * stride < nunits) {
+        Acc acc[PP][VE];
 #pragma unroll
-        for (int v = 0; v < VE; ++v) o.v[v] = FromAcc<T, Acc>::f(acc[i][v]);
-        *reinterpret_cast<uint4*>(Cb + cOff[i] + u * VE) = *reinterpret_cast<uint4*>(&o);
+        for (int i = 0; i < PP; ++i)
+#pragma unroll
+          for (int v = 0; v < VE; ++v) acc[i][v] = acc_zero((Acc*)nullptr);
+#pragma unroll
+        for (int k = 0; k < KK; ++k)
+          if (k < p.K) {
+#pragma unroll
+            for (int v = 0; v < VE; ++v) {
+              const Acc xv = to_acc(x[j][k].v[v]);
+#pragma unroll
+              for (int i = 0; i < PP; ++i) fma_acc(acc[i][v], w[k][i], xv);
+            }
+          }
+#pragma unroll
+        for (int i = 0; i < PP; ++i)
+          if (i < p.P) {
+            Pack o;
+#pragma unroll
+            for (int v = 0; v < VE; ++v) o.v[v] = FromAcc<T, Acc>::f(acc[i][v]);
+            *reinterpret_cast<uint4*>(Cb + co[i] + (u0 + j * stride) * VE) = *reinterpret_cast<uint4*>(&o);
+          }
       }
   }
 }
@@ -375,8 +392,13 @@ static int launch_simt(int mode, const ThinParams& p, cudaStream_t st) {
   using Acc = typename DType<DT>::Acc;
   constexpr int VE = 16 / (int)sizeof(T);
   if (mode == 0) {
+    const int kk = p.K <= 2 ? 2 : (p.K <= 4 ? 4 : 8), pp = p.P <= 2 ? 2 : (p.P <= 4 ? 4 : 8);
     dim3 grid(thin_grid_x(p.L / VE, p.batch, 8), (unsigned)p.batch);
-    thin_simt_a_kernel<T, Acc><<<grid, 256, 0, st>>>(p);
+#define TNB_THIN_A(KK, PP) if (kk == KK && pp == PP) thin_simt_a_kernel<T, Acc, KK, PP><<<grid, 256, 0, st>>>(p);
+    TNB_THIN_A(2, 2) TNB_THIN_A(2, 4) TNB_THIN_A(2, 8)
+    TNB_THIN_A(4, 2) TNB_THIN_A(4, 4) TNB_THIN_A(4, 8)
+    TNB_THIN_A(8, 2) TNB_THIN_A(8, 4) TNB_THIN_A(8, 8)
+#undef TNB_THIN_A
     TNB_LAUNCH_CHECK();
     count_launch();
     set_kernel_name("thin_simt_a");

@@ -91,3 +91,24 @@ def test_path_known_answers():
   labels = [["e%d" % i, "e%d" % (i + 1)] for i in range(4)]
   sizes = {"e%d" % i: d[i] for i in range(5)}
   assert nn.greedy_path(labels, ["e0", "e4"], sizes) == [(0, 1), (0, 2), (0, 1)]
+
+
+def test_blocksparse_oracle_matches_reference_data_vectors():
+  """oracle/np_blocksparse.py (cpu_baseline of the cfg-4 bench leg) against the real reference's result data
+  vectors for the trailing-axes cases of tests/golden/blocksparse.npz (incl. cfg 4 itself)."""
+  from oracle import np_blocksparse as nbs
+  meta, z = load_golden("blocksparse")
+  checked = 0
+  for ci, m in enumerate(meta):
+    n = len(m["axes"][0])
+    trailing = list(range(m["nlegs"] - n, m["nlegs"]))
+    if m["perm"] is not None or m["axes"][0] != trailing or m["axes"][1] != trailing:
+      continue
+    charges = [z["c%d_q%d" % (ci, li)] for li in range(m["nlegs"])]
+    flows = list(m["flows"])
+    a = z["c%d_A" % ci]
+    assert a.shape[0] == nbs.num_nonzero(charges, flows)
+    c, _, _ = nbs.tensordot_trailing(a, charges, flows, np.conj(a), charges, [not f for f in flows], n)
+    np.testing.assert_allclose(c, z["c%d_C" % ci], rtol=1e-12, atol=1e-12)
+    checked += 1
+  assert checked >= 3
