@@ -80,16 +80,26 @@ class ClockSampler(threading.Thread):
     self.stop_flag = False
 
   def run(self):
-    while not self.stop_flag:
-      try:
-        out = subprocess.run(["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                              "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-        f = [x.strip() for x in out.strip().split(",")]
+    # one long-running nvidia-smi in loop mode (a fresh process per sample costs ~50 ms and would see
+    # one or two samples of a 100 ms timed region)
+    try:
+      proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                               "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:  # pylint: disable=broad-except
+      return
+    try:
+      for line in proc.stdout:
+        f = [x.strip() for x in line.strip().split(",")]
         if len(f) >= 8:
           self.samples.append(f)
+        if self.stop_flag:
+          break
+    finally:
+      proc.terminate()
+      try:
+        proc.wait(timeout=2)
       except Exception:  # pylint: disable=broad-except
-        pass
-      time.sleep(0.05)
+        proc.kill()
 
   def summary(self):
     if not self.samples:
@@ -158,7 +168,8 @@ def workload_config(args, world):
                       % (L_SITES, BOND, PHYS),
           "networks_per_step_per_gpu": max(1, args.networks), "launch_mode": "eager" if args.no_graph else "cuda-graph replay", "compute_dtype": args.dtype, "path_provider": "numpy greedy (opt_einsum stand-in)",
           "parallelism": "replicas x%d (independent MPS samples, no collective)" % world,
-          "l2_policy": "inputs (128 tensors) exceed the 126 MB L2 for f32/f64; bf16 inputs are 134 MB"}
+          "l2_policy": "no flush needed: one step reads %d x 128 input tensors = %.1f GB (bf16: 134 MB per network), far beyond the 126 MB L2"
+                       % (max(1, args.networks), max(1, args.networks) * 0.134 * {"bf16": 1, "f32": 2, "f64": 4}[args.dtype])}
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -169,7 +180,7 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--impl", default="cuda_b200", choices=["cuda_b200", "reference"])
   ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32", "f64"])
-  ap.add_argument("--networks", type=int, default=8,
+  ap.add_argument("--networks", type=int, default=74,
                   help="independent MPS samples contracted in lock-step per step per GPU (batched kernels)")
   ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
   ap.add_argument("--cpu-baseline-steps", type=int, default=2)
@@ -194,6 +205,8 @@ def main():
   import torch
   import torch.distributed as dist
   if world > 1:
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
+      os.environ["NCCL_DEBUG"] = "WARN"           # rank 0's stdout carries exactly one JSON line
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
   torch.cuda.set_device(local)
   import tensornetwork_b200 as tb
@@ -221,11 +234,14 @@ def main():
     t = be.randn(shapes[i], np.float32, seed=1 + 7919 * rank + i)
     t *= 1.0 / np.sqrt(dims[i] * PHYS)
     kets.append(be.astype(t, {"bf16": "bfloat16", "f32": np.float32, "f64": np.float64}[args.dtype]))
-  dev = kets + [be.copy(k) for k in kets]                       # bra = conj(ket) (real data): its own 64 tensors
-  h2d_bytes = sum(int(np.prod(s)) * esize for s in shapes)
+  # bra = conj(ket): the reference's caller builds it on the backend (`tn.conj(node)`); for real data conj is the
+  # identity, so the 64 bra inputs are views of the ket buffers (conj_aliases) and only the kets cross PCIe
+  dev = kets + list(kets)
+  aliases = {L_SITES + i: i for i in range(L_SITES)}
+  h2d_bytes = sum(int(np.prod(s)) * esize for s in shapes[:L_SITES])
 
   net = drivers.CompiledNetwork(be, shapes, {"bf16": "bfloat16", "f32": np.float32, "f64": np.float64}[args.dtype],
-                                labels, [], path=path, nbatch=nbatch) if not args.no_graph else None
+                                labels, [], path=path, nbatch=nbatch, conj_aliases=aliases) if not args.no_graph else None
   host = None
   if net is not None:
     net.load(dev)
@@ -233,9 +249,10 @@ def main():
     # region, with the same synthetic data; a user would generate / load their data straight into these views)
     host = net.host_staging()
     for dst, src in zip(host, dev):
-      dst.copy_(src.t)
+      if dst is not None:
+        dst.copy_(src.t)
   else:
-    host = [d.t.cpu().pin_memory() for d in dev]
+    host = [d.t.cpu().pin_memory() for d in kets]
   torch.cuda.synchronize()
 
   def step_resident():
@@ -248,7 +265,7 @@ def main():
       out = net.run_staged()    # ONE H2D of the pinned staging arena (all inputs), then graph replay
     else:
       ts = [tb.B200Tensor(h.to(be.device, non_blocking=True), code) for h in host]
-      out = drivers.contract_network(ts, labels, [], path=path, backend=be, nbatch=nbatch)
+      out = drivers.contract_network(ts + ts, labels, [], path=path, backend=be, nbatch=nbatch)
     return out.t.to("cpu")      # D2H of the result (one scalar per network; syncs)
 
   def barrier():
@@ -274,6 +291,27 @@ def main():
   sampler.stop_flag = True
   sampler.join(timeout=2)
   result_value = [float(x) for x in np.atleast_1d(res.to_host().astype(np.float64))]
+
+  # ---- latency of ONE network (no sample batching): the same plan compiled for a single MPS sample
+  single = None
+  if nbatch and net is not None:
+    one = [tb.B200Tensor(d.t[0], code) for d in dev]
+    net1 = drivers.CompiledNetwork(be, core_shapes, {"bf16": "bfloat16", "f32": np.float32, "f64": np.float64}[args.dtype],
+                                   labels, [], path=path, nbatch=0, conj_aliases=aliases)
+    net1.load(one)
+    for _ in range(3):
+      net1()
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(args.steps):
+      net1()
+    s1.record()
+    torch.cuda.synchronize()
+    ms1 = s0.elapsed_time(s1) / args.steps
+    single = {"ms_per_network": ms1, "contractions_per_s": npair / (ms1 * 1e-3), "launches": net1.launches_per_replay,
+              "note": "one network per graph replay (127 dependent launches, latency-bound)"}
+    del net1, one
 
   # ---- per-kernel device times of one step (live, CUDA events) -> dominant kernel and its roofline
   kstats = kernel_profile(be, dev, labels, path, work, nbatch, NB, esize)
@@ -365,6 +403,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "result_check": result_value[:4],
+        "single_network": single,
     }
     if not args.no_cpu_baseline and world == 1:
       line["cpu_baseline"] = cpu_baseline(args)

@@ -407,7 +407,7 @@ class CompiledNetwork:
   overwritten by the next call (clone it to keep it)."""
 
   def __init__(self, backend, shapes, dtype, labels, out_labels=(), path=None, nbatch=0,
-               algorithm=None, num_streams=4):
+               algorithm=None, num_streams=4, conj_aliases=None):
     from . import tensor as T  # pylint: disable=import-outside-toplevel
     from .tensor import B200Tensor  # pylint: disable=import-outside-toplevel
     self.backend = backend
@@ -425,11 +425,24 @@ class CompiledNetwork:
     # staging arena, so a step's host->device transfer is a single cudaMemcpyAsync
     tdt = T.code_to_torch(code)
     esz = torch.empty((), dtype=tdt).element_size()
+    # conj_aliases {i: j}: input i is conj(input j) — e.g. the bra layer of <psi|psi>, which the reference
+    # builds on the backend with `tn.conj(node)`.  For real dtypes conj is the identity, so input i is a
+    # VIEW of input j's static buffer (as torch's lazy conj is): nothing is staged or copied for it.
+    self._alias = dict(conj_aliases or {})
+    if self._alias and code in (T.C64, T.C128):
+      raise NotImplementedError("conj_aliases are views and therefore limited to real dtypes")
+    for i, j in self._alias.items():
+      if j in self._alias or tuple(shapes[i]) != tuple(shapes[j]):
+        raise ValueError("conj_aliases must map to a non-aliased input of the same shape")
     offs, tot = [], 0
-    for shp in shapes:
+    for i, shp in enumerate(shapes):
+      if i in self._alias:
+        offs.append(None)
+        continue
       n = int(np.prod(shp)) if len(shp) else 1
       offs.append(tot)
       tot += (n * esz + 255) // 256 * 256
+    offs = [offs[self._alias[i]] if i in self._alias else o for i, o in enumerate(offs)]
     self._arena = torch.zeros(max(tot, 256), dtype=torch.uint8, device=backend.device)
     self._host_arena = None
     self._offs, self._esz, self._tdt, self._shapes = offs, esz, tdt, [tuple(s) for s in shapes]
@@ -465,7 +478,10 @@ class CompiledNetwork:
     if self._host_arena is None:
       self._host_arena = torch.zeros(self._arena.numel(), dtype=torch.uint8).pin_memory()
       self._host_views = []
-      for shp, off in zip(self._shapes, self._offs):
+      for i, (shp, off) in enumerate(zip(self._shapes, self._offs)):
+        if i in self._alias:
+          self._host_views.append(None)           # a view of another input: nothing to stage
+          continue
         n = int(np.prod(shp)) if len(shp) else 1
         self._host_views.append(self._host_arena[off:off + n * self._esz].view(self._tdt).view(shp))
     return self._host_views
@@ -478,7 +494,9 @@ class CompiledNetwork:
 
   def load(self, tensors):
     """copy inputs (B200Tensor, torch tensors or pinned host tensors) into the static buffers"""
-    for dst, src in zip(self.inputs, tensors):
+    for i, (dst, src) in enumerate(zip(self.inputs, tensors)):
+      if i in self._alias or src is None:
+        continue
       t = src.t if isinstance(src, B200Tensor) else src
       dst.t.copy_(t, non_blocking=True)
 

@@ -136,3 +136,51 @@ def test_cfg2_mps_norm_small_sizes_and_properties():
   ref = nn.contract_path(ts, labels, path, [])
   out = drivers.contract_network(ts, labels, [], path=path, backend=be)
   assert_close(out, ref, tol=1e-10)
+
+
+def _norm_network(L, D, d=2):
+  dims = [1] + [min(D, d**min(i, L - i)) for i in range(1, L)] + [1]
+  labels = []
+  for side in "kb":
+    for i in range(L):
+      labels.append(["e0" if i == 0 else "%s%d" % (side, i), "p%d" % i, "eL" if i == L - 1 else "%s%d" % (side, i + 1)])
+  return dims, labels
+
+
+# float32 runs on the tensor cores as TF32 (2^-11 input rounding per pairwise step); the ket and bra halves make the
+# same rounding errors, so over the ~2L dependent steps they add coherently: stated tolerance 3e-2 on the scalar
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-10), ("float32", 3e-2)])
+def test_compiled_network_graph_replay_staging_and_aliases(dtype, tol):
+  """CUDA-graph CompiledNetwork (what bench.py times): batched samples, pinned staging arena, bra layer as
+  conj-alias views of the ket buffers; every replay must equal the oracle's pairwise contraction per sample."""
+  import torch
+  from tensornetwork_b200 import drivers
+  be = get_backend()
+  rng = np.random.default_rng(13)
+  L, D, NB = 12, 32, 3
+  dims, labels = _norm_network(L, D)
+  core = [(dims[i], 2, dims[i + 1]) for i in range(L)] * 2
+  shapes = [(NB,) + s for s in core]
+  sizes = {l: s[ax] for s, labs in zip(core, labels) for ax, l in enumerate(labs)}
+  path = nn.greedy_path(labels, [], sizes)
+  net = drivers.CompiledNetwork(be, shapes, np.dtype(dtype), labels, [], path=path, nbatch=1,
+                                conj_aliases={L + i: i for i in range(L)})
+  host = net.host_staging()
+  assert all(host[L + i] is None for i in range(L))
+  for rep in range(2):                                 # second replay with fresh data through the same graph
+    kets = [(rng.standard_normal((NB,) + core[i]) / np.sqrt(core[i][0] * 2)).astype(dtype) for i in range(L)]
+    for i in range(L):
+      host[i].copy_(torch.from_numpy(kets[i]))
+    out = net.run_staged().to_host()
+    for b in range(NB):
+      ts = [k[b].astype(np.float64) for k in kets]
+      ref = nn.contract_path(ts + [np.conj(t) for t in ts], labels, path, [])
+      assert abs(out[b] - ref) <= tol * abs(ref), (dtype, rep, b, out[b], ref)
+  # unbatched graph fed from device tensors via load(); explicit (non-aliased) bra inputs
+  net1 = drivers.CompiledNetwork(be, core, np.dtype(dtype), labels, [], path=path, nbatch=0)
+  ts = [k[0] for k in kets]
+  dev = [be.convert_to_tensor(t) for t in ts + [np.conj(t) for t in ts]]
+  out1 = net1(dev).to_host()
+  ref = nn.contract_path([t.astype(np.float64) for t in ts] + [np.conj(t).astype(np.float64) for t in ts], labels, path, [])
+  assert abs(float(out1) - ref) <= tol * abs(ref)
+  assert net1.launches_per_replay >= len(path)
