@@ -314,7 +314,10 @@ def main():
     del net1, one
 
   # ---- per-kernel device times of one step (live, CUDA events) -> dominant kernel and its roofline
-  kstats = kernel_profile(be, dev, labels, path, work, nbatch, NB, esize)
+  if net is not None and getattr(net, "_nodes", None) is not None:
+    kstats = net.profile(work, NB, esize)          # the nodes the graph replays (a chained launch is one node)
+  else:
+    kstats = kernel_profile(be, dev, labels, path, work, nbatch, NB, esize)
 
   # ---- end-to-end timing (host buffers) ----------------------------------------------
   for _ in range(args.warmup):
@@ -381,7 +384,8 @@ def main():
         "note": "dominant kernel timed live with CUDA events around each of its launches (eager replay of the "
                 "step); algorithmic bytes = operands + result once, algorithmic flops = 2MNK; the binding roof "
                 "is the one with the larger minimum time",
-        "families": {k: {"launches": round(v["launches"], 2), "us": round(v["us"], 1),
+        "families": {k: {"launches": round(v["launches"], 2), "pairwise_steps": round(v.get("pairwise_steps", v["launches"]), 2),
+                         "us": round(v["us"], 1),
                          "tflops": round(v["flops"] / (v["us"] * 1e-6) / 1e12, 1),
                          "gbs": round(v["bytes"] / (v["us"] * 1e-6) / 1e9, 1)} for k, v in kstats.items()},
     })

@@ -192,6 +192,26 @@ TNB200_API int32_t tnb200_svd_batched(const void* a_data, int32_t dtype, int32_t
 TNB200_API int32_t tnb200_gather(const void* src, const int64_t* idx_dev, void* dst, int64_t n, int32_t dtype,
                                  int32_t scatter, void* stream);
 
+/* ---- a8/a9: a RUN of dependent pairwise contractions of one path (the sequential `contract_between` loop of
+ * contractors/opt_einsum_paths/path_contractors.py:87-90, e.g. the MPS zipper) as ONE persistent launch.
+ * Step i is the contraction tnb200_tensordot(a, b, c, ...) would perform; dep_a / dep_b name the earlier step
+ * of the chain whose output `c` is this step's operand (or -1 when the operand exists before the launch).
+ * Every step must be a tensor-core GEMM addressable in place (M >= 256, N >= 128, 16/32-bit float, one batch
+ * mode shared by all steps); otherwise create() returns TNB200_ERR_UNSUPPORTED with *first_unsupported = the
+ * offending step and the caller launches the steps one by one.  create() allocates device tables (not
+ * capturable); launch() is stream-ordered and capturable; operand addresses are frozen at create(). */
+typedef struct {
+  tnb200_tensor_t a, b, c;
+  int32_t naxes, nbatch;
+  int32_t axes_a[TNB200_MAX_NDIM], axes_b[TNB200_MAX_NDIM];
+  int32_t batch_a[TNB200_MAX_NDIM], batch_b[TNB200_MAX_NDIM];
+  int32_t dep_a, dep_b;
+} tnb200_chain_step_t;
+TNB200_API int32_t tnb200_chain_create(int32_t nsteps, const tnb200_chain_step_t* steps, int32_t* first_unsupported,
+                                       void** handle);
+TNB200_API int32_t tnb200_chain_launch(void* handle, void* stream);
+TNB200_API int32_t tnb200_chain_destroy(void* handle);
+
 #ifdef __cplusplus
 }
 #endif

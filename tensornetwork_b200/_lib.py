@@ -27,6 +27,14 @@ class TensorDesc(ctypes.Structure):
               ("shape", ctypes.c_int64 * MAX_NDIM), ("stride", ctypes.c_int64 * MAX_NDIM)]
 
 
+class ChainStep(ctypes.Structure):
+  """tnb200_chain_step_t"""
+  _fields_ = [("a", TensorDesc), ("b", TensorDesc), ("c", TensorDesc), ("naxes", ctypes.c_int32), ("nbatch", ctypes.c_int32),
+              ("axes_a", ctypes.c_int32 * MAX_NDIM), ("axes_b", ctypes.c_int32 * MAX_NDIM),
+              ("batch_a", ctypes.c_int32 * MAX_NDIM), ("batch_b", ctypes.c_int32 * MAX_NDIM),
+              ("dep_a", ctypes.c_int32), ("dep_b", ctypes.c_int32)]
+
+
 _P = ctypes.POINTER(TensorDesc)
 _i32, _i64, _u64, _dbl, _vp = (ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double,
                                ctypes.c_void_p)
@@ -62,6 +70,9 @@ SIGNATURES = {
     "tnb200_gather": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp]),
     "tnb200_blocksparse_tensordot": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp,
                                             _vp, _vp, _i64, _i64, _i32, _vp]),
+    "tnb200_chain_create": (_i32, [_i32, ctypes.POINTER(ChainStep), _pi32, ctypes.POINTER(_vp)]),
+    "tnb200_chain_launch": (_i32, [_vp, _vp]),
+    "tnb200_chain_destroy": (_i32, [_vp]),
 }
 
 _lib = None

@@ -169,7 +169,7 @@ class CudaB200Backend(_Base):
         raise ValueError("shape-mismatch for sum")
     return self._contract(a, b, ax_a, ax_b, [], [], conj_a, conj_b)
 
-  def _contract(self, a, b, ax_a, ax_b, bat_a, bat_b, conj_a=False, conj_b=False):
+  def _contract(self, a, b, ax_a, ax_b, bat_a, bat_b, conj_a=False, conj_b=False, out=None):
     if a.code != b.code:
       code = self._promote(a.code, b.code)
       a, b = self.astype(a, code), self.astype(b, code)
@@ -182,7 +182,12 @@ class CudaB200Backend(_Base):
     used_a, used_b = set(na) | set(ba), set(nb) | set(bb)
     out_shape = [sa[i] for i in ba] + [sa[i] for i in range(nda) if i not in used_a] + \
         [sb[i] for i in range(ndb) if i not in used_b]
-    c = self._new(out_shape, a.code)
+    if out is None:
+      c = self._new(out_shape, a.code)
+    else:                                   # preallocated result (static buffers of a compiled network)
+      if tuple(out.shape) != tuple(out_shape) or out.code != a.code:
+        raise ValueError("out has shape {} / dtype code {}, expected {} / {}".format(out.shape, out.code, out_shape, a.code))
+      c = out
     flags = (L.CONJ_A if conj_a else 0) | (L.CONJ_B if conj_b else 0) | self.math_mode
     rc = self.lib.tnb200_tensordot(a.ref(), b.ref(), c.ref(), len(na), _i32arr(na), _i32arr(nb),
                                    len(ba), _i32arr(ba), _i32arr(bb), flags, self._stream())

@@ -33,6 +33,11 @@ struct GemmProblem {
 // meet the kernel's layout/alignment constraints; the planner then repacks or falls back.
 int gemm_tcgen05(const GemmProblem& p, cudaStream_t st);   // bf16 / f16 / f32(tf32)
 int gemm_dmma_f64(const GemmProblem& p, cudaStream_t st);  // f64 via mma.sync DMMA
+// Chained GEMMs in one persistent launch (gemm_tcgen05.cu): dep_a[i] / dep_b[i] = index of the chain step whose
+// output is step i's operand A / B (or -1).  create() allocates device tables (call it outside stream capture).
+int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, const int* dep_b, void** handle);
+int gemm_chain_launch(void* handle, cudaStream_t st);
+int gemm_chain_destroy(void* handle);
 // can the TMA/UMMA path address this operand view in place?  (tile-size independent check)
 bool tcgen05_view_ok(int dtype, const OperandView& v, int64_t ext_f, int64_t ext_k, int64_t batch);
 

@@ -18,6 +18,7 @@
 #include "gemm.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <vector>
 
 namespace tnb {
 
@@ -714,6 +715,81 @@ static int encode_operand(CUtensorMap* map, int dtype, const OperandView& v, int
   return 0;
 }
 
+struct TcPrep {
+  TcParams p;
+  CUtensorMap tmA, tmB;
+  bool use2;
+  int stage_bytes, b_rows;
+};
+
+// Tile selection, tensor maps and instruction descriptor of one GEMM.  chain_mode: the problem is one step of a
+// chained launch (gemm_tcgen05_chain_kernel): always 2-CTA pair tiles with the widest BN the problem fills.
+static int tc_prepare(const GemmProblem& g, bool chain_mode, TcPrep& o) {
+  TcParams& p = o.p;
+  const int es = es_of(g.dtype);
+  const int sms = num_sms();
+  const int64_t tiles_m = (g.M + kBM - 1) / kBM;
+  int BN = 64;   // multiples of 64 so that an MN-major B tile is a whole number of 128-byte chunks
+  if (g.swapped) {
+    // tiny N: 32 columns suffice unless the (MN-major) B tile needs whole 128-byte chunks
+    const bool b_unit_f = g.B.nF == 0 || g.B.fs[g.B.nF - 1] == 1;
+    const bool b_unit_k = g.K == 1 || g.B.nK == 0 || g.B.ks[g.B.nK - 1] == 1;
+    BN = (g.N <= 32 && (b_unit_k || (b_unit_f && es == 4))) ? 32 : 64;
+  } else {
+    const int cands[3] = {256, 128, 64};
+    for (int i = 0; i < 3; ++i) {
+      int bn = cands[i];
+      if (bn > 64 && bn / 2 >= g.N) continue;          // tile mostly empty
+      int64_t tiles = tiles_m * ((g.N + bn - 1) / bn) * g.batch;
+      if (tiles >= sms || bn == 64) { BN = bn; break; }
+    }
+    if (chain_mode) BN = g.N >= 256 ? 256 : 128;
+  }
+  // 2-CTA pairs (256 x BN tiles) for problems large enough to fill the GPU with pair tiles
+  static int force2 = -2;
+  if (force2 == -2) { const char* e = getenv("TNB200_2CTA"); force2 = e ? (e[0] == '0' ? 0 : 1) : -1; }
+  bool use2 = false;
+  if (g.M >= 256 && BN >= 128 && !g.swapped) {
+    const int64_t pair_tiles = ((g.M + 2 * kBM - 1) / (2 * kBM)) * ((g.N + BN - 1) / BN) * g.batch;
+    use2 = force2 == 1 || (force2 == -1 && BN == 256 && pair_tiles >= sms / 2);
+  }
+  if (force2 == 0) use2 = false;
+  if (chain_mode) {
+    if (g.swapped || g.M < 256 || g.N < 128) return TNB200_ERR_UNSUPPORTED;
+    use2 = true;
+  }
+  p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
+  p.BN = BN;
+  const int bk = kRowBytes / es;
+  p.num_kb = (int)((g.K + bk - 1) / bk);
+  p.tiles_m = use2 ? (g.M + 2 * kBM - 1) / (2 * kBM) : tiles_m;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  p.num_tiles = p.tiles_m * p.tiles_n * g.batch;
+  const int b_rows = use2 ? BN / 2 : BN;                   // B rows staged per CTA per k-block
+  const int stage_bytes = kBM * kRowBytes + b_rows * kRowBytes;
+  int stages = (196 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > p.num_kb + 1 && p.num_tiles <= sms) stages = p.num_kb + 1 > 2 ? p.num_kb + 1 : 2;
+  p.stages = stages;
+  p.out_kind = g.dtype == TNB200_BF16 ? 0 : (g.dtype == TNB200_F16 ? 1 : 2);
+  p.C = g.C; p.c_sm = g.c_sm; p.c_sb = g.c_sb; p.c_cs = g.swapped ? g.c_sn : 1;
+  if (g.swapped && p.c_cs == 1) p.c_cs = 2;   // degenerate (M == 1): force the transposed-store path; stride unused
+  p.vec_ok = !g.swapped && (((uintptr_t)g.C) % 16 == 0) && ((g.c_sm * es) % 16 == 0) && ((g.c_sb * es) % 16 == 0);
+    bool a_mn = false, b_mn = false;
+  int rc = encode_operand(&o.tmA, g.dtype, g.A, g.M, g.K, g.batch, kBM, a_mn, p.a_fe, p.a_ke);
+  if (rc) return rc;
+  rc = encode_operand(&o.tmB, g.dtype, g.B, g.N, g.K, g.batch, b_rows, b_mn, p.b_fe, p.b_ke);
+  if (rc) return rc;
+  p.a_mn = a_mn; p.b_mn = b_mn;
+  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B format, majors, N>>3, M>>4
+  const uint32_t fmt = g.dtype == TNB200_BF16 ? 1u : (g.dtype == TNB200_F16 ? 0u : 2u);
+  const uint32_t mma_m = use2 ? 256u : 128u;
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+            ((uint32_t)(BN >> 3) << 17) | ((mma_m >> 4) << 24);
+  o.use2 = use2; o.stage_bytes = stage_bytes; o.b_rows = b_rows;
+  return 0;
+}
+
 int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
   if (g.dtype != TNB200_F32 && g.dtype != TNB200_F16 && g.dtype != TNB200_BF16) return TNB200_ERR_UNSUPPORTED;
   {
@@ -737,63 +813,17 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
     t.c_sm = g.c_sn; t.c_sn = g.c_sm;          // row stride of C^T = column stride of C (1)
     return gemm_tcgen05(t, st);
   }
-  const int es = es_of(g.dtype);
+  TcPrep prep;
+  {
+    int rc = tc_prepare(g, false, prep);
+    if (rc) return rc;
+  }
+  const TcParams& p = prep.p;
+  const CUtensorMap& tmA = prep.tmA;
+  const CUtensorMap& tmB = prep.tmB;
+  const bool use2 = prep.use2;
+  const int stages = p.stages, stage_bytes = prep.stage_bytes;
   const int sms = num_sms();
-  const int64_t tiles_m = (g.M + kBM - 1) / kBM;
-  int BN = 64;   // multiples of 64 so that an MN-major B tile is a whole number of 128-byte chunks
-  if (g.swapped) {
-    // tiny N: 32 columns suffice unless the (MN-major) B tile needs whole 128-byte chunks
-    const bool b_unit_f = g.B.nF == 0 || g.B.fs[g.B.nF - 1] == 1;
-    const bool b_unit_k = g.K == 1 || g.B.nK == 0 || g.B.ks[g.B.nK - 1] == 1;
-    BN = (g.N <= 32 && (b_unit_k || (b_unit_f && es == 4))) ? 32 : 64;
-  } else {
-    const int cands[3] = {256, 128, 64};
-    for (int i = 0; i < 3; ++i) {
-      int bn = cands[i];
-      if (bn > 64 && bn / 2 >= g.N) continue;          // tile mostly empty
-      int64_t tiles = tiles_m * ((g.N + bn - 1) / bn) * g.batch;
-      if (tiles >= sms || bn == 64) { BN = bn; break; }
-    }
-  }
-  // 2-CTA pairs (256 x BN tiles) for problems large enough to fill the GPU with pair tiles
-  static int force2 = -2;
-  if (force2 == -2) { const char* e = getenv("TNB200_2CTA"); force2 = e ? (e[0] == '0' ? 0 : 1) : -1; }
-  bool use2 = false;
-  if (g.M >= 256 && BN >= 128 && !g.swapped) {
-    const int64_t pair_tiles = ((g.M + 2 * kBM - 1) / (2 * kBM)) * ((g.N + BN - 1) / BN) * g.batch;
-    use2 = force2 == 1 || (force2 == -1 && BN == 256 && pair_tiles >= sms / 2);
-  }
-  if (force2 == 0) use2 = false;
-  TcParams p;
-  p.M = g.M; p.N = g.N; p.K = g.K; p.batch = g.batch;
-  p.BN = BN;
-  const int bk = kRowBytes / es;
-  p.num_kb = (int)((g.K + bk - 1) / bk);
-  p.tiles_m = use2 ? (g.M + 2 * kBM - 1) / (2 * kBM) : tiles_m;
-  p.tiles_n = (g.N + BN - 1) / BN;
-  p.num_tiles = p.tiles_m * p.tiles_n * g.batch;
-  const int b_rows = use2 ? BN / 2 : BN;                   // B rows staged per CTA per k-block
-  const int stage_bytes = kBM * kRowBytes + b_rows * kRowBytes;
-  int stages = (196 * 1024) / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages > p.num_kb + 1 && p.num_tiles <= sms) stages = p.num_kb + 1 > 2 ? p.num_kb + 1 : 2;
-  p.stages = stages;
-  p.out_kind = g.dtype == TNB200_BF16 ? 0 : (g.dtype == TNB200_F16 ? 1 : 2);
-  p.C = g.C; p.c_sm = g.c_sm; p.c_sb = g.c_sb; p.c_cs = g.swapped ? g.c_sn : 1;
-  if (g.swapped && p.c_cs == 1) p.c_cs = 2;   // degenerate (M == 1): force the transposed-store path; stride unused
-  p.vec_ok = !g.swapped && (((uintptr_t)g.C) % 16 == 0) && ((g.c_sm * es) % 16 == 0) && ((g.c_sb * es) % 16 == 0);
-  CUtensorMap tmA, tmB;
-  bool a_mn = false, b_mn = false;
-  int rc = encode_operand(&tmA, g.dtype, g.A, g.M, g.K, g.batch, kBM, a_mn, p.a_fe, p.a_ke);
-  if (rc) return rc;
-  rc = encode_operand(&tmB, g.dtype, g.B, g.N, g.K, g.batch, b_rows, b_mn, p.b_fe, p.b_ke);
-  if (rc) return rc;
-  p.a_mn = a_mn; p.b_mn = b_mn;
-  // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B format, majors, N>>3, M>>4
-  const uint32_t fmt = g.dtype == TNB200_BF16 ? 1u : (g.dtype == TNB200_F16 ? 0u : 2u);
-  const uint32_t mma_m = use2 ? 256u : 128u;
-  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-            ((uint32_t)(BN >> 3) << 17) | ((mma_m >> 4) << 24);
   const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * 8 + 32 + 4 * kSlabBytes + 1024;
   const int kind = g.dtype == TNB200_F32 ? 1 : 0;
   static bool attr_set[4] = {false, false, false, false};
@@ -820,6 +850,357 @@ int gemm_tcgen05(const GemmProblem& g, cudaStream_t st) {
   count_launch();
   if (use2) set_kernel_name(g.dtype == TNB200_BF16 ? "tcgen05_2cta_bf16" : (g.dtype == TNB200_F16 ? "tcgen05_2cta_f16" : "tcgen05_2cta_tf32"));
   else set_kernel_name(g.dtype == TNB200_BF16 ? "tcgen05_bf16" : (g.dtype == TNB200_F16 ? "tcgen05_f16" : "tcgen05_tf32"));
+  return 0;
+}
+
+int gemm_chain_destroy(void* handle);
+
+// =====================================================================================
+// Chained GEMMs in ONE persistent launch (cta_group::2 pair tiles only).
+//
+// A contraction path often contains long runs of dependent GEMMs (the MPS "zipper": E' = A^T (E A) per site).
+// Launched one by one, every step pays the persistent kernel's prologue + drain, and every intermediate makes
+// a round trip through HBM (the cfg-2 bulk step is HBM-bound: 184 flop/B).  Here all steps of such a run are
+// tiles of ONE kernel: the tile sequence is ordered so that a small group of samples is carried through the
+// whole run of steps before the next group starts (intermediates are produced and consumed while still in
+// L2), and inter-step dependencies are tracked per (step, sample) with release/acquire counters in global
+// memory: an epilogue warp publishes its part of an output tile with red.release, the TMA producer of a
+// dependent tile spins with ld.acquire + fence.proxy.async before its first load.  Tiles are assigned to
+// CTA pairs round-robin in sequence order and all CTAs are co-resident (grid <= SM count), so a tile only
+// ever waits for tiles that are earlier in the sequence: no deadlock.
+struct alignas(64) ChainStepDev {
+  CUtensorMap tmA, tmB;
+  TcParams p;
+  int dep_a, dep_b;               // chain step that produces operand a / b (-1: available before the launch)
+  uint32_t need_a, need_b;        // counter value of that step's (sample) entry when it is complete
+  int tiles_per_sample;
+  uint32_t tx_bytes;              // bytes landing on the leader's full barrier per k-block (both CTAs)
+};
+struct ChainSeg { long long tile0; int step, sample0, nsamples, pad; };
+struct ChainParams {
+  const ChainStepDev* steps;
+  const ChainSeg* segs;
+  uint32_t* done;                 // [nsteps][batch] completion counters (zeroed before every launch)
+  long long num_tiles;
+  int nsegs, batch, stages, stage_bytes;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add_u32(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// bounded spin on a dependency counter (a scheduling bug traps instead of hanging the box)
+__device__ __forceinline__ void chain_wait(const uint32_t* ctr, uint32_t need) {
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    if (ld_acquire_u32(ctr) >= need) return;
+    __nanosleep(64);
+  }
+  __trap();
+}
+
+struct ChainTile { int step, bi, mi, ni; };
+__device__ __forceinline__ const ChainStepDev* chain_decode(const ChainParams& cp, long long tile, int& cursor, ChainTile& t) {
+  while (cursor + 1 < cp.nsegs && tile >= cp.segs[cursor + 1].tile0) ++cursor;
+  const ChainSeg sg = cp.segs[cursor];
+  const ChainStepDev* sd = cp.steps + sg.step;
+  uint32_t local = (uint32_t)(tile - sg.tile0);
+  const uint32_t tn = (uint32_t)sd->p.tiles_n, tm = (uint32_t)sd->p.tiles_m;
+  t.ni = (int)(local % tn); local /= tn;
+  t.mi = (int)(local % tm);
+  t.bi = sg.sample0 + (int)(local / tm);
+  t.step = sg.step;
+  return sd;
+}
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tcgen05_chain_kernel(const __grid_constant__ ChainParams cp) {
+  constexpr int ES = KIND == 0 ? 2 : 4;
+  constexpr int BK = kRowBytes / ES;
+  constexpr int CHUNK = kRowBytes / ES;
+  constexpr int A_BYTES = kBM * kRowBytes;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int STAGE_BYTES = cp.stage_bytes;
+  const int S = cp.stages;
+  uint64_t* bars = (uint64_t*)(smem + (size_t)S * STAGE_BYTES);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+  const uint32_t epi_slab = (smem_u32(tmem_slot) + 16 + 15) & ~15u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long first = blockIdx.x >> 1, step = gridDim.x >> 1;   // pair index / number of pairs
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (both CTAs, whole warp)
+    int s = 0; uint32_t ph = 0;
+    int cursor = 0;
+    for (long long tile = first; tile < cp.num_tiles; tile += step) {
+      ChainTile t;
+      const ChainStepDev* sd = chain_decode(cp, tile, cursor, t);
+      const int BN = sd->p.BN, b_rows = BN / 2;
+      const int a_mn = sd->p.a_mn, b_mn = sd->p.b_mn;
+      const int nA = a_mn ? kBM / CHUNK : 1;
+      const int nB = b_mn ? b_rows / CHUNK : 1;
+      const bool mine = lane < nA + nB;
+      const bool is_a = lane < nA;
+      const int c = is_a ? lane : lane - nA;
+      const bool mn = is_a ? (a_mn != 0) : (b_mn != 0);
+      const uint32_t fe = is_a ? sd->p.a_fe : sd->p.b_fe, ke = is_a ? sd->p.a_ke : sd->p.b_ke;
+      const CUtensorMap* map = is_a ? &sd->tmA : &sd->tmB;
+      const uint32_t dst_off = (is_a ? 0u : (uint32_t)A_BYTES) + (mn ? (uint32_t)c * (BK * kRowBytes) : 0u);
+      int f;
+      if (is_a) f = t.mi * 2 * kBM + (int)rank * kBM + (mn ? c * CHUNK : 0);
+      else f = t.ni * BN + (int)rank * b_rows + (mn ? c * CHUNK : 0);
+      const int f_in = fe ? (int)((uint32_t)f % fe) : f, f_out = fe ? (int)((uint32_t)f / fe) : 0;
+      const int num_kb = sd->p.num_kb;
+      const uint32_t tx = sd->tx_bytes;
+      // operands produced by earlier steps of this launch: wait until every tile of (that step, this sample) is out
+      if (lane == 0) {
+        if (sd->dep_a >= 0) chain_wait(cp.done + (size_t)sd->dep_a * cp.batch + t.bi, sd->need_a);
+        if (sd->dep_b >= 0) chain_wait(cp.done + (size_t)sd->dep_b * cp.batch + t.bi, sd->need_b);
+      }
+      __syncwarp();
+      asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy writes (other SMs' epilogues) -> our TMA reads
+      int k_in = 0, k_out = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t full = full_bar(s);
+        if (lane == 0) {
+          if (leader) mbar_expect_tx(full, tx);
+          else mbar_arrive_remote(full, 0);
+        }
+        __syncwarp();
+        if (mine) {
+          const uint32_t dst = smem_u32(smem + (size_t)s * STAGE_BYTES) + dst_off;
+          if (!mn) tma_load_5d_2sm(dst, map, full, k_in, f_in, f_out, k_out, t.bi);
+          else     tma_load_5d_2sm(dst, map, full, f_in, k_in, k_out, f_out, t.bi);
+        }
+        k_in += BK;
+        if (ke && (uint32_t)k_in >= ke) { k_in = 0; ++k_out; }
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================================================== MMA issuer (leader CTA only)
+    int s = 0; uint32_t ph = 0;
+    int acc = 0; uint32_t acc_ph = 0;
+    int cursor = 0;
+    for (long long tile = first; tile < cp.num_tiles; tile += step) {
+      ChainTile t;
+      const ChainStepDev* sd = chain_decode(cp, tile, cursor, t);
+      const int a_mn = sd->p.a_mn, b_mn = sd->p.b_mn, num_kb = sd->p.num_kb;
+      const uint32_t idesc = sd->p.idesc;
+      const uint32_t a_layout = (a_mn && KIND == 1) ? 1u : 2u;
+      const uint32_t b_layout = (b_mn && KIND == 1) ? 1u : 2u;
+      const uint32_t a_lbo = a_mn ? BK * kRowBytes : 0u, b_lbo = b_mn ? BK * kRowBytes : 0u;
+      const uint32_t a_sbo = (a_mn && KIND == 1) ? 512u : 1024u;
+      const uint32_t b_sbo = (b_mn && KIND == 1) ? 512u : 1024u;
+      const uint32_t a_kstep = a_mn ? (32u / ES) * kRowBytes : 32u;
+      const uint32_t b_kstep = b_mn ? (32u / ES) * kRowBytes : 32u;
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, a_layout);
+          const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, b_layout);
+          tc_mma_2sm<KIND>(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit_2sm(empty_bar(s));
+        if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(acc));
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (both CTAs: their own 128 rows)
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_ph = 0;
+    int cursor = 0;
+    for (long long tile = first; tile < cp.num_tiles; tile += step) {
+      ChainTile t;
+      const ChainStepDev* sd = chain_decode(cp, tile, cursor, t);
+      const TcParams p = sd->p;                              // per-step output description (registers / local)
+      const int64_t row = (int64_t)t.mi * 2 * kBM + (int64_t)rank * kBM + q * 32 + lane;
+      const int64_t n0 = (int64_t)t.ni * p.BN;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      epilogue_drain(p, taddr0, p.BN, t.bi, row - lane, lane, n0, epi_slab + (uint32_t)q * kSlabBytes);
+      tc_fence_before();
+      __threadfence();                                       // this lane's stores are visible device-wide ...
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0);
+        red_release_add_u32(cp.done + (size_t)t.step * cp.batch + t.bi, 1u);   // ... before the tile part is published
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------- chain: host side
+struct ChainHandle {
+  ChainStepDev* d_steps = nullptr;
+  ChainSeg* d_segs = nullptr;
+  uint32_t* d_done = nullptr;
+  ChainParams cp;
+  int kind = 0, nsteps = 0;
+  size_t smem = 0, done_bytes = 0;
+  unsigned grid = 0;
+  double flops = 0.0;
+};
+
+int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, const int* dep_b, void** handle) {
+  *handle = nullptr;
+  if (nsteps < 1) return TNB200_ERR_INVALID;
+  {
+    static int disabled = -1;
+    if (disabled < 0) { const char* e = getenv("TNB200_NO_CHAIN"); disabled = (e && e[0] == '1') ? 1 : 0; }
+    if (disabled) return TNB200_ERR_UNSUPPORTED;
+  }
+  const int dtype = probs[0].dtype;
+  const int64_t batch = probs[0].batch;
+  std::vector<ChainStepDev> steps(nsteps);
+  int max_stage = 0, max_tps = 1;
+  double flops = 0.0;
+  for (int i = 0; i < nsteps; ++i) {
+    const GemmProblem& g = probs[i];
+    if (g.dtype != dtype || g.batch != batch || g.conjA || g.conjB) return TNB200_ERR_UNSUPPORTED;
+    if (g.dtype != TNB200_F32 && g.dtype != TNB200_F16 && g.dtype != TNB200_BF16) return TNB200_ERR_UNSUPPORTED;
+    if (g.c_sn != 1 || g.M >= (1LL << 31) || g.N >= (1LL << 31) || g.K >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
+    if (dep_a[i] >= i || dep_b[i] >= i) return TNB200_ERR_INVALID;
+    TcPrep prep;
+    int rc = tc_prepare(g, true, prep);
+    if (rc) return rc;
+    ChainStepDev& sd = steps[i];
+    sd.tmA = prep.tmA; sd.tmB = prep.tmB; sd.p = prep.p;
+    sd.dep_a = dep_a[i]; sd.dep_b = dep_b[i];
+    sd.tiles_per_sample = (int)(prep.p.tiles_m * prep.p.tiles_n);
+    sd.tx_bytes = (uint32_t)(2 * prep.stage_bytes);
+    sd.need_a = sd.need_b = 0;
+    if (prep.stage_bytes > max_stage) max_stage = prep.stage_bytes;
+    if (sd.tiles_per_sample > max_tps) max_tps = sd.tiles_per_sample;
+    flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)batch;
+  }
+  for (int i = 0; i < nsteps; ++i) {
+    if (steps[i].dep_a >= 0) steps[i].need_a = 8u * (uint32_t)steps[steps[i].dep_a].tiles_per_sample;   // 2 CTAs x 4 epilogue warps per tile
+    if (steps[i].dep_b >= 0) steps[i].need_b = 8u * (uint32_t)steps[steps[i].dep_b].tiles_per_sample;
+  }
+  // ---- tile sequence: rounds of (rot x G) samples are carried depth-first through all steps; inside a round the
+  // rot sub-groups alternate so that a step's tiles are separated from their producers by (rot - 1) sub-groups
+  const int sms = num_sms();
+  const int pairs = sms / 2;
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+  int G = env_int("TNB200_CHAIN_G", pairs / max_tps);
+  if (G < 1) G = 1;
+  int rot = env_int("TNB200_CHAIN_ROT", 3);
+  if (rot < 1) rot = 1;
+  std::vector<ChainSeg> segs;
+  long long tile0 = 0;
+  for (int64_t r0 = 0; r0 < batch; r0 += (int64_t)G * rot) {
+    const int64_t r1 = r0 + (int64_t)G * rot < batch ? r0 + (int64_t)G * rot : batch;
+    for (int i = 0; i < nsteps; ++i)
+      for (int sub = 0; sub < rot; ++sub) {
+        const int64_t s0 = r0 + (int64_t)sub * G, s1 = s0 + G < r1 ? s0 + G : r1;
+        if (s0 >= s1) continue;
+        ChainSeg sg;
+        sg.tile0 = tile0; sg.step = i; sg.sample0 = (int)s0; sg.nsamples = (int)(s1 - s0); sg.pad = 0;
+        segs.push_back(sg);
+        tile0 += (long long)(s1 - s0) * steps[i].tiles_per_sample;
+      }
+  }
+  int stages = (196 * 1024) / max_stage;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return TNB200_ERR_UNSUPPORTED;
+  ChainHandle* h = new ChainHandle();
+  h->kind = dtype == TNB200_F32 ? 1 : 0;
+  h->nsteps = nsteps;
+  h->flops = flops;
+  h->done_bytes = sizeof(uint32_t) * (size_t)nsteps * (size_t)batch;
+  cudaError_t e = cudaMalloc(&h->d_steps, sizeof(ChainStepDev) * steps.size());
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_segs, sizeof(ChainSeg) * segs.size());
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_done, h->done_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_steps, steps.data(), sizeof(ChainStepDev) * steps.size(), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(h->d_segs, segs.data(), sizeof(ChainSeg) * segs.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    set_error("chain: device table allocation failed: %s", cudaGetErrorString(e));
+    cudaFree(h->d_steps); cudaFree(h->d_segs); cudaFree(h->d_done);
+    delete h;
+    return TNB200_ERR_CUDA;
+  }
+  h->cp.steps = h->d_steps; h->cp.segs = h->d_segs; h->cp.done = h->d_done;
+  h->cp.num_tiles = tile0; h->cp.nsegs = (int)segs.size(); h->cp.batch = (int)batch;
+  h->cp.stages = stages; h->cp.stage_bytes = max_stage;
+  h->smem = (size_t)stages * max_stage + (2 * stages + 4) * 8 + 32 + 4 * kSlabBytes + 1024;
+  const long long np = tile0 < pairs ? tile0 : pairs;
+  h->grid = (unsigned)(2 * np);
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[h->kind]) {
+    e = h->kind == 0 ? cudaFuncSetAttribute(gemm_tcgen05_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                     : cudaFuncSetAttribute(gemm_tcgen05_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) { set_error("chain: cannot raise dynamic smem: %s", cudaGetErrorString(e)); gemm_chain_destroy(h); return TNB200_ERR_CUDA; }
+    attr_set[h->kind] = true;
+  }
+  *handle = h;
+  return 0;
+}
+
+int gemm_chain_launch(void* handle, cudaStream_t st) {
+  ChainHandle* h = (ChainHandle*)handle;
+  if (!h) return TNB200_ERR_INVALID;
+  TNB_CHECK_CUDA(cudaMemsetAsync(h->d_done, 0, h->done_bytes, st));
+  if (h->kind == 0) gemm_tcgen05_chain_kernel<0><<<h->grid, kThreads, h->smem, st>>>(h->cp);
+  else gemm_tcgen05_chain_kernel<1><<<h->grid, kThreads, h->smem, st>>>(h->cp);
+  TNB_LAUNCH_CHECK();
+  count_launch();
+  set_kernel_name(h->kind == 0 ? "tcgen05_chain_16" : "tcgen05_chain_tf32");
+  return 0;
+}
+
+int gemm_chain_destroy(void* handle) {
+  ChainHandle* h = (ChainHandle*)handle;
+  if (!h) return 0;
+  cudaFree(h->d_steps); cudaFree(h->d_segs); cudaFree(h->d_done);
+  delete h;
   return 0;
 }
 

@@ -288,11 +288,12 @@ static int pack_operand(int dt, const void* src, const ModeList& mB, int wb, con
 
 using namespace tnb;
 
-extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tensor_t* b,
-                                    const tnb200_tensor_t* c, int32_t naxes, const int32_t* axes_a,
-                                    const int32_t* axes_b, int32_t nbatch, const int32_t* batch_a,
-                                    const int32_t* batch_b, int32_t flags, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
+namespace tnb {
+// Validate a contraction request and classify its axes into batch / free-A (M) / free-B (N) / contracted (K)
+// mode lists (np.tensordot output order: batch axes, free axes of a, free axes of b).
+int build_modes(const tnb200_tensor_t* a, const tnb200_tensor_t* b, const tnb200_tensor_t* c, int32_t naxes,
+                const int32_t* axes_a, const int32_t* axes_b, int32_t nbatch, const int32_t* batch_a,
+                const int32_t* batch_b, ModeList& mB, ModeList& mM, ModeList& mN, ModeList& mK) {
   TNB_REQUIRE(valid_tensor(a) && valid_tensor(b) && valid_tensor(c), TNB200_ERR_INVALID,
               "tensordot: invalid tensor descriptor");
   TNB_REQUIRE(a->dtype == b->dtype && a->dtype == c->dtype, TNB200_ERR_DTYPE,
@@ -301,7 +302,7 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
   TNB_REQUIRE(naxes >= 0 && nbatch >= 0 && naxes + nbatch <= a->ndim && naxes + nbatch <= b->ndim,
               TNB200_ERR_INVALID, "tensordot: too many axes");
   int role_a[TNB200_MAX_NDIM] = {0}, role_b[TNB200_MAX_NDIM] = {0};  // 0 free, 1 summed, 2 batch
-  ModeList mB, mM, mN, mK;
+  mB = ModeList(); mM = ModeList(); mN = ModeList(); mK = ModeList();
   for (int i = 0; i < naxes; ++i) {
     int x = axes_a[i], y = axes_b[i];
     if (x < 0) x += a->ndim;
@@ -343,6 +344,62 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
   TNB_REQUIRE(cax == c->ndim, TNB200_ERR_INVALID, "tensordot: output rank mismatch (%d vs %d)", cax,
               c->ndim);
 
+  return 0;
+}
+
+// Lower a contraction to a GEMM whose operands are BOTH addressable in place by the TMA / tcgen05 path
+// (no repack, no skinny / thin special case).  Used by the chained-GEMM planner (gemm_chain.cu).
+int plan_inplace_gemm(const tnb200_tensor_t* a, const tnb200_tensor_t* b, const tnb200_tensor_t* c, int32_t naxes,
+                      const int32_t* axes_a, const int32_t* axes_b, int32_t nbatch, const int32_t* batch_a,
+                      const int32_t* batch_b, GemmProblem& g) {
+  ModeList mB, mM, mN, mK;
+  int rc = build_modes(a, b, c, naxes, axes_a, axes_b, nbatch, batch_a, batch_b, mB, mM, mN, mK);
+  if (rc) return rc;
+  const int dt = a->dtype;
+  if (dt != TNB200_F32 && dt != TNB200_F16 && dt != TNB200_BF16) return TNB200_ERR_UNSUPPORTED;
+  const int64_t M = mM.total(), N = mN.total(), K = mK.total(), Bt = mB.total();
+  if (M == 0 || N == 0 || Bt == 0 || K == 0) return TNB200_ERR_UNSUPPORTED;
+  ModeList gB = mB, gM = mM, gN = mN;
+  merge_modes(gB, 3); merge_modes(gM, 2); merge_modes(gN, 2);
+  if (gB.n > 1) return TNB200_ERR_UNSUPPORTED;
+  int64_t cm_ext, cm_s, cn_ext, cn_s;
+  ModeList cM, cN;
+  for (int i = 0; i < gM.n; ++i) cM.push(gM.ext[i], gM.s1[i]);
+  for (int i = 0; i < gN.n; ++i) cN.push(gN.ext[i], gN.s1[i]);
+  if (!(single_mode(cM, 0, cm_ext, cm_s) && single_mode(cN, 0, cn_ext, cn_s))) return TNB200_ERR_UNSUPPORTED;
+  g = GemmProblem();
+  g.dtype = dt; g.M = M; g.N = N; g.K = K; g.batch = Bt;
+  g.C = c->data; g.c_sm = cm_s; g.c_sn = cn_s; g.c_sb = gB.n ? gB.s2[0] : 0;
+  for (int cand = 0; cand < 2; ++cand) {
+    ModeList ko = order_k(mK, cand);
+    merge_modes(ko, 2);
+    if (ko.n > 4 || gM.n > 4 || gN.n > 4) continue;
+    OperandView va, vb;
+    va.ptr = a->data; vb.ptr = b->data;
+    va.nF = gM.n; for (int i = 0; i < gM.n; ++i) { va.fe[i] = gM.ext[i]; va.fs[i] = gM.s0[i]; }
+    vb.nF = gN.n; for (int i = 0; i < gN.n; ++i) { vb.fe[i] = gN.ext[i]; vb.fs[i] = gN.s0[i]; }
+    va.nK = vb.nK = ko.n;
+    for (int i = 0; i < ko.n; ++i) { va.ke[i] = vb.ke[i] = ko.ext[i]; va.ks[i] = ko.s0[i]; vb.ks[i] = ko.s1[i]; }
+    va.sb = gB.n ? gB.s0[0] : 0; vb.sb = gB.n ? gB.s1[0] : 0;
+    if (tcgen05_view_ok(dt, va, M, K, Bt) && tcgen05_view_ok(dt, vb, N, K, Bt)) {
+      g.A = va; g.B = vb;
+      return 0;
+    }
+  }
+  return TNB200_ERR_UNSUPPORTED;
+}
+}  // namespace tnb
+
+extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tensor_t* b,
+                                    const tnb200_tensor_t* c, int32_t naxes, const int32_t* axes_a,
+                                    const int32_t* axes_b, int32_t nbatch, const int32_t* batch_a,
+                                    const int32_t* batch_b, int32_t flags, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  ModeList mB, mM, mN, mK;
+  {
+    int rc = build_modes(a, b, c, naxes, axes_a, axes_b, nbatch, batch_a, batch_b, mB, mM, mN, mK);
+    if (rc) return rc;
+  }
   const int dt = a->dtype;
   const bool conjA = (flags & TNB200_CONJ_A) && dtype_is_complex(dt);
   const bool conjB = (flags & TNB200_CONJ_B) && dtype_is_complex(dt);
@@ -467,3 +524,33 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
   merge_modes(gK, 2);
   return dispatch_simt(dt, a->data, b->data, c->data, gB, gM, gN, gK, conjA, conjB, st);
 }
+
+// ------------------------------------------------------------------------------------------ chained contractions
+extern "C" int32_t tnb200_chain_create(int32_t nsteps, const tnb200_chain_step_t* steps, int32_t* first_unsupported,
+                                       void** handle) {
+  TNB_REQUIRE(nsteps >= 1 && steps && handle, TNB200_ERR_INVALID, "chain: bad arguments");
+  *handle = nullptr;
+  if (first_unsupported) *first_unsupported = -1;
+  std::vector<GemmProblem> probs((size_t)nsteps);
+  std::vector<int> da((size_t)nsteps), db((size_t)nsteps);
+  for (int i = 0; i < nsteps; ++i) {
+    const tnb200_chain_step_t& s = steps[i];
+    int rc = plan_inplace_gemm(&s.a, &s.b, &s.c, s.naxes, s.axes_a, s.axes_b, s.nbatch, s.batch_a, s.batch_b, probs[i]);
+    if (rc) { if (first_unsupported) *first_unsupported = i; return rc; }
+    da[i] = s.dep_a; db[i] = s.dep_b;
+    TNB_REQUIRE(s.dep_a < i && s.dep_b < i, TNB200_ERR_INVALID, "chain: step %d depends on a later step", i);
+    TNB_REQUIRE(s.dep_a < 0 || steps[s.dep_a].c.data == s.a.data, TNB200_ERR_INVALID, "chain: dep_a of step %d does not produce its operand", i);
+    TNB_REQUIRE(s.dep_b < 0 || steps[s.dep_b].c.data == s.b.data, TNB200_ERR_INVALID, "chain: dep_b of step %d does not produce its operand", i);
+  }
+  // tile-shape eligibility is per step: report the first step the chained kernel cannot take
+  for (int i = 0; i < nsteps; ++i) {
+    const GemmProblem& g = probs[i];
+    if (g.M < 256 || g.N < 128 || g.batch != probs[0].batch || g.dtype != probs[0].dtype) {
+      if (first_unsupported) *first_unsupported = i;
+      return TNB200_ERR_UNSUPPORTED;
+    }
+  }
+  return gemm_chain_create(nsteps, probs.data(), da.data(), db.data(), handle);
+}
+extern "C" int32_t tnb200_chain_launch(void* handle, void* stream) { return gemm_chain_launch(handle, (cudaStream_t)stream); }
+extern "C" int32_t tnb200_chain_destroy(void* handle) { return gemm_chain_destroy(handle); }

@@ -397,6 +397,62 @@ def plan_path(shapes, labels, path, out_labels, nbatch=0):
   return steps, res
 
 
+def plan_shapes(shapes, steps):
+  """output shape of every slot of a path plan (inputs first, then one slot per step)"""
+  shp = [tuple(s) for s in shapes]
+  for st in steps:
+    op = st[0]
+    if op == "tensordot":
+      a, b = shp[st[1]], shp[st[2]]
+      out = [x for i, x in enumerate(a) if i not in st[3]] + [x for i, x in enumerate(b) if i not in st[4]]
+    elif op == "batched":
+      a, b = shp[st[1]], shp[st[2]]
+      ua, ub = set(st[3]) | set(st[5]), set(st[4]) | set(st[6])
+      out = [a[i] for i in st[5]] + [x for i, x in enumerate(a) if i not in ua] + [x for i, x in enumerate(b) if i not in ub]
+    elif op == "transpose":
+      out = [shp[st[1]][p] for p in st[2]]
+    else:
+      raise NotImplementedError("plan_shapes: step kind " + str(op))
+    shp.append(tuple(out))
+  return shp
+
+
+def find_chains(steps, n_inputs, min_len=2):
+  """Maximal runs of CONSECUTIVE contraction steps in which every step consumes the previous step's result:
+  candidates for one chained launch (tnb200_chain_create).  Returns lists of step indices."""
+  runs, cur = [], []
+  for idx, st in enumerate(steps):
+    ok = st[0] in ("tensordot", "batched")
+    if ok and cur and (n_inputs + cur[-1]) in (st[1], st[2]):
+      cur.append(idx)
+      continue
+    if len(cur) >= min_len:
+      runs.append(cur)
+    cur = [idx] if ok else []
+  if len(cur) >= min_len:
+    runs.append(cur)
+  return runs
+
+
+class _Chain:
+  """A created chained launch: owns the library handle; `steps` are the plan step indices it covers."""
+
+  def __init__(self, backend, handle, step_ids):
+    self.backend, self.handle, self.steps = backend, handle, list(step_ids)
+
+  def launch(self):
+    from . import _lib as L  # pylint: disable=import-outside-toplevel
+    L.check(self.backend.lib.tnb200_chain_launch(self.handle, self.backend._stream()))  # pylint: disable=protected-access
+
+  def __del__(self):
+    try:
+      if self.handle:
+        self.backend.lib.tnb200_chain_destroy(self.handle)
+        self.handle = None
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+
 class CompiledNetwork:
   """A network contraction frozen into a CUDA graph (the `jit` of this backend).
 
@@ -407,7 +463,7 @@ class CompiledNetwork:
   overwritten by the next call (clone it to keep it)."""
 
   def __init__(self, backend, shapes, dtype, labels, out_labels=(), path=None, nbatch=0,
-               algorithm=None, num_streams=4, conj_aliases=None):
+               algorithm=None, num_streams=4, conj_aliases=None, use_chains=True):
     from . import tensor as T  # pylint: disable=import-outside-toplevel
     from .tensor import B200Tensor  # pylint: disable=import-outside-toplevel
     self.backend = backend
@@ -429,7 +485,7 @@ class CompiledNetwork:
     # builds on the backend with `tn.conj(node)`.  For real dtypes conj is the identity, so input i is a
     # VIEW of input j's static buffer (as torch's lazy conj is): nothing is staged or copied for it.
     self._alias = dict(conj_aliases or {})
-    if self._alias and code in (T.C64, T.C128):
+    if self._alias and T.is_complex_code(code):
       raise NotImplementedError("conj_aliases are views and therefore limited to real dtypes")
     for i, j in self._alias.items():
       if j in self._alias or tuple(shapes[i]) != tuple(shapes[j]):
@@ -452,24 +508,224 @@ class CompiledNetwork:
       view = self._arena[off:off + n * esz].view(tdt).view(tuple(shp))
       self.inputs.append(B200Tensor(view, code))
     self.num_pairwise = len(path)
+    self.streams = [torch.cuda.Stream() for _ in range(max(1, num_streams))]
+    self._nodes = None
+    use_static = use_chains and all(st[0] in ("tensordot", "batched", "transpose") for st in self.steps)
+    if use_static:
+      self._build_static(code)
     # warm-up on a side stream (loads kernels, sets function attributes), then capture
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-      execute_plan(backend, self.inputs, self.steps, self.res_slot)
+      if self._nodes is not None:
+        self._run_nodes([side])
+      else:
+        execute_plan(backend, self.inputs, self.steps, self.res_slot)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     self.graph = torch.cuda.CUDAGraph()
-    self.streams = [torch.cuda.Stream() for _ in range(max(1, num_streams))]
     l0 = backend.lib.tnb200_launch_count()
     with torch.cuda.graph(self.graph):
-      if num_streams > 1:
+      if self._nodes is not None:
+        self.output = self._run_nodes(self.streams)
+      elif num_streams > 1:
         # keep every intermediate alive until capture ends: no buffer is recycled across streams
         self.output, self._keep = execute_plan_streams(backend, self.inputs, self.steps, self.res_slot,
                                                        self.streams)
       else:
         self.output = execute_plan(backend, self.inputs, self.steps, self.res_slot)
     self.launches_per_replay = int(backend.lib.tnb200_launch_count() - l0)
+
+  # ------------------------------------------------------------------ static plan with chained launches
+  def _build_static(self, code):
+    """Preallocate every step's result (addresses must be known before capture: chained launches freeze their
+    operand pointers at creation) and group the plan into nodes: single steps and chains."""
+    import ctypes  # pylint: disable=import-outside-toplevel
+    from . import _lib as L  # pylint: disable=import-outside-toplevel
+    be = self.backend
+    n_in = len(self.inputs)
+    shp = plan_shapes(self._shapes, self.steps)
+    vals = list(self.inputs)
+    for i, st in enumerate(self.steps):
+      if st[0] == "transpose":
+        vals.append(be.transpose(vals[st[1]], st[2]))
+      else:
+        vals.append(be._new(shp[n_in + i], code))  # pylint: disable=protected-access
+    self._vals = vals
+    chain_of = {}
+    self.chains = []
+    pending = find_chains(self.steps, n_in)
+    while pending:
+      run = pending.pop(0)
+      if len(run) < 2:
+        continue
+      pos = {sid: k for k, sid in enumerate(run)}
+      arr = (L.ChainStep * len(run))()
+      for k, sid in enumerate(run):
+        st = self.steps[sid]
+        a, b, c = vals[st[1]], vals[st[2]], vals[n_in + sid]
+        cs = arr[k]
+        cs.a, cs.b, cs.c = a.desc(), b.desc(), c.desc()
+        if st[0] == "tensordot":
+          ax_a, ax_b, ba, bb = st[3], st[4], (), ()
+        else:
+          ax_a, ax_b, ba, bb = st[3], st[4], st[5], st[6]
+        cs.naxes, cs.nbatch = len(ax_a), len(ba)
+        for j, x in enumerate(ax_a):
+          cs.axes_a[j] = x
+        for j, x in enumerate(ax_b):
+          cs.axes_b[j] = x
+        for j, x in enumerate(ba):
+          cs.batch_a[j] = x
+        for j, x in enumerate(bb):
+          cs.batch_b[j] = x
+        # operands that are (views of) results of earlier steps of this run
+        cs.dep_a = self._producer(st[1], n_in, pos)
+        cs.dep_b = self._producer(st[2], n_in, pos)
+      handle = ctypes.c_void_p()
+      bad = ctypes.c_int32(-1)
+      rc = be.lib.tnb200_chain_create(len(run), arr, ctypes.byref(bad), ctypes.byref(handle))
+      if rc == 0:
+        ch = _Chain(be, handle, run)
+        self.chains.append(ch)
+        for sid in run:
+          chain_of[sid] = ch
+      elif rc == L.ERR_UNSUPPORTED:
+        k = bad.value if bad.value >= 0 else 0      # split the run around the step the kernel cannot take
+        pending[:0] = [run[:k], run[k + 1:]]
+      else:
+        L.check(rc)
+    nodes, seen = [], set()
+    for i, st in enumerate(self.steps):
+      ch = chain_of.get(i)
+      if ch is None:
+        nodes.append(("step", i))
+      elif id(ch) not in seen:
+        seen.add(id(ch))
+        nodes.append(("chain", ch))
+    self._nodes = nodes
+
+  def _producer(self, slot, n_in, pos):
+    """position (inside the run `pos`) of the step that produced `slot`, looking through transposes; -1 if outside"""
+    while slot >= n_in and self.steps[slot - n_in][0] == "transpose":
+      slot = self.steps[slot - n_in][1]
+    return pos.get(slot - n_in, -1) if slot >= n_in else -1
+
+  def _node_io(self, node):
+    n_in = len(self.inputs)
+    if node[0] == "step":
+      st = self.steps[node[1]]
+      ins = [st[1], st[2]] if st[0] != "transpose" else [st[1]]
+      return ins, [n_in + node[1]]
+    outs = [n_in + sid for sid in node[1].steps]
+    ins = []
+    for sid in node[1].steps:
+      st = self.steps[sid]
+      ins += [x for x in (st[1], st[2]) if x not in outs]
+    return ins, outs
+
+  def _launch_node(self, node):
+    be, n_in, vals = self.backend, len(self.inputs), self._vals
+    if node[0] == "chain":
+      node[1].launch()
+      return
+    st = self.steps[node[1]]
+    if st[0] == "tensordot":
+      be._contract(vals[st[1]], vals[st[2]], list(st[3]), list(st[4]), [], [], out=vals[n_in + node[1]])  # pylint: disable=protected-access
+    elif st[0] == "batched":
+      be._contract(vals[st[1]], vals[st[2]], list(st[3]), list(st[4]), list(st[5]), list(st[6]),  # pylint: disable=protected-access
+                   out=vals[n_in + node[1]])
+
+  def _run_nodes(self, streams):
+    """dependency-aware execution of the node list on `streams` (the structure execute_plan_streams uses); all
+    chained launches share streams[0]: two persistent chain kernels must never wait for each other's SMs."""
+    torch = self.backend.torch
+    main = torch.cuda.current_stream()
+    multi = len(streams) > 1 or streams[0] is not main
+    n_in = len(self.inputs)
+    home, events = {}, {}
+    if multi:
+      for s in streams:
+        s.wait_stream(main)
+    rr = 0
+    for node in self._nodes:
+      ins, outs = self._node_io(node)
+      if node[0] == "step" and self.steps[node[1]][0] == "transpose":      # a view: inherits its operand's stream
+        src = ins[0]
+        if src in home:
+          home[outs[0]] = home[src]
+          events[outs[0]] = events[src]
+        continue
+      produced = [i for i in ins if i in home]
+      if node[0] == "chain":
+        si = 0
+      elif not produced:
+        si = rr % len(streams)
+        rr += 1
+      else:
+        si = home[max(produced)]
+      stream = streams[si]
+      for i in produced:
+        if home[i] != si:
+          stream.wait_event(events[i])
+      with torch.cuda.stream(stream):
+        self._launch_node(node)
+        e = torch.cuda.Event()
+        e.record(stream)
+      for o in outs:
+        home[o] = si
+        events[o] = e
+    if multi:
+      for s in streams:
+        main.wait_stream(s)
+    return self._vals[self.res_slot]
+
+  def profile(self, work, nb, esize, reps=3):
+    """Per-kernel-family device time of one replay, measured live with CUDA events around every node of the
+    static plan (a chained launch is one node).  `work` = (M, K, N) of every pairwise step in plan order.
+    Bytes are algorithmic: operands + result of a step once; for a chain, only what enters and leaves the launch."""
+    torch = self.backend.torch
+    if self._nodes is None:
+      raise RuntimeError("profile() needs the static plan (use_chains=True)")
+    n_in = len(self.inputs)
+    cidx, k = {}, 0
+    for i, st in enumerate(self.steps):
+      if st[0] != "transpose":
+        cidx[i] = k
+        k += 1
+    numel = lambda slot: float(np.prod(self._vals[slot].shape[self.nbatch:]) if self._vals[slot].shape[self.nbatch:] else 1.0)
+    stats = {}
+    for rep in range(reps + 1):
+      evs = []
+      for node in self._nodes:
+        if node[0] == "step" and self.steps[node[1]][0] == "transpose":
+          continue
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._launch_node(node)
+        e1.record()
+        name = self.backend.lib.tnb200_last_kernel().decode()
+        ins, outs = self._node_io(node)
+        sids = [node[1]] if node[0] == "step" else node[1].steps
+        flops = sum(2.0 * work[cidx[s]][0] * work[cidx[s]][1] * work[cidx[s]][2] for s in sids)
+        if node[0] == "step":
+          m, kk, n = work[cidx[node[1]]]
+          byts = float(m * kk + kk * n + m * n)
+        else:
+          ext_out = [o for o in outs if o == self.res_slot or any(o in self._node_io(nd)[0] for nd in self._nodes if nd is not node)]
+          byts = sum(numel(i) for i in set(ins)) + sum(numel(o) for o in ext_out)
+        evs.append((name, e0, e1, flops * nb, byts * nb * esize, len(sids)))
+      torch.cuda.synchronize()
+      if rep == 0:
+        continue
+      for name, e0, e1, fl, by, nst in evs:
+        d = stats.setdefault(name, {"launches": 0.0, "us": 0.0, "flops": 0.0, "bytes": 0.0, "pairwise_steps": 0.0})
+        d["launches"] += 1.0 / reps
+        d["us"] += e0.elapsed_time(e1) * 1e3 / reps
+        d["flops"] += fl / reps
+        d["bytes"] += by / reps
+        d["pairwise_steps"] += nst / reps
+    return stats
 
   def host_staging(self):
     """Pinned host views (one torch tensor per input) carved from a single staging arena.  Fill them

@@ -92,6 +92,16 @@ class FakeLib:
     C[...] = np.einsum("".join(sa) + "," + "".join(sb) + "->" + out, A, B)
     return 0
 
+  def tnb200_chain_create(self, nsteps, steps, first_unsupported, handle):
+    self._err = b"chained launches need the CUDA library"
+    return -4
+
+  def tnb200_chain_launch(self, handle, stream):
+    return -1
+
+  def tnb200_chain_destroy(self, handle):
+    return 0
+
   def tnb200_copy(self, src, dst, conj, stream):
     s, d = _view(src), _view(dst)
     self._launches += 1

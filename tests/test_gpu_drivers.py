@@ -184,3 +184,37 @@ def test_compiled_network_graph_replay_staging_and_aliases(dtype, tol):
   ref = nn.contract_path([t.astype(np.float64) for t in ts] + [np.conj(t).astype(np.float64) for t in ts], labels, path, [])
   assert abs(float(out1) - ref) <= tol * abs(ref)
   assert net1.launches_per_replay >= len(path)
+
+
+@pytest.mark.parametrize("dtype,tol", [("bfloat16", 6e-2), ("float32", 3e-2)])
+def test_chained_launch_equals_stepwise(dtype, tol):
+  """The MPS zipper of a D=256 norm network as ONE chained persistent launch (tnb200_chain_*) must reproduce the
+  step-by-step graph bit for bit (same tiles, same k order, same rounding) and the oracle within the dtype's
+  tolerance; replays must be stable (dependency counters are reset by every launch)."""
+  import torch
+  from tensornetwork_b200 import drivers
+  be = get_backend()
+  rng = np.random.default_rng(17)
+  L, D, NB = 24, 256, 5
+  dims, labels = _norm_network(L, D)
+  core = [(dims[i], 2, dims[i + 1]) for i in range(L)] * 2
+  shapes = [(NB,) + s for s in core]
+  sizes = {l: s[ax] for s, labs in zip(core, labels) for ax, l in enumerate(labs)}
+  path = nn.greedy_path(labels, [], sizes)
+  kets = [(rng.standard_normal((NB,) + core[i]) / np.sqrt(core[i][0] * 2)).astype(np.float32) for i in range(L)]
+  dev = [be.astype(be.convert_to_tensor(k), dtype) for k in kets]
+  al = {L + i: i for i in range(L)}
+  net_c = drivers.CompiledNetwork(be, shapes, dtype, labels, [], path=path, nbatch=1, conj_aliases=al, use_chains=True)
+  net_s = drivers.CompiledNetwork(be, shapes, dtype, labels, [], path=path, nbatch=1, conj_aliases=al, use_chains=False)
+  assert net_c.chains and max(len(c.steps) for c in net_c.chains) >= 4, "no chain was formed"
+  assert net_c.launches_per_replay < net_s.launches_per_replay
+  net_c.load(dev + [None] * L)
+  net_s.load(dev + [None] * L)
+  ref = net_s().to_host().astype(np.float64)
+  for rep in range(3):
+    out = net_c().to_host().astype(np.float64)
+    np.testing.assert_array_equal(out, ref)
+  for b in range(NB):
+    ts = [d.to_host()[b].astype(np.float64) for d in dev]
+    exact = nn.contract_path(ts + [np.conj(t) for t in ts], labels, path, [])
+    assert abs(out[b] - exact) <= tol * abs(exact), (dtype, b, out[b], exact)
