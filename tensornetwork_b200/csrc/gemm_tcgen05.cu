@@ -1100,7 +1100,7 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
   const int dtype = probs[0].dtype;
   const int64_t batch = probs[0].batch;
   std::vector<ChainStepDev> steps(nsteps);
-  int max_stage = 0, max_tps = 1;
+  int max_stage = 0;
   double flops = 0.0;
   for (int i = 0; i < nsteps; ++i) {
     const GemmProblem& g = probs[i];
@@ -1118,21 +1118,27 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
     sd.tx_bytes = (uint32_t)(2 * prep.stage_bytes);
     sd.need_a = sd.need_b = 0;
     if (prep.stage_bytes > max_stage) max_stage = prep.stage_bytes;
-    if (sd.tiles_per_sample > max_tps) max_tps = sd.tiles_per_sample;
     flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)batch;
   }
   for (int i = 0; i < nsteps; ++i) {
     if (steps[i].dep_a >= 0) steps[i].need_a = 8u * (uint32_t)steps[steps[i].dep_a].tiles_per_sample;   // 2 CTAs x 4 epilogue warps per tile
     if (steps[i].dep_b >= 0) steps[i].need_b = 8u * (uint32_t)steps[steps[i].dep_b].tiles_per_sample;
   }
-  // ---- tile sequence: rounds of (rot x G) samples are carried depth-first through all steps; inside a round the
-  // rot sub-groups alternate so that a step's tiles are separated from their producers by (rot - 1) sub-groups
+  // ---- tile sequence.  The batch is cut into rounds of G samples and every round is carried through ALL steps
+  // before the next one starts, so a step's results are consumed soon after they are produced; a round must be
+  // wide enough that a dependent tile is >= 2 full waves of tiles behind its producers (TMA runs ~1 tile ahead
+  // of the MMA, the epilogue ~1 tile behind: measured on cfg 2, G = 9 -> 8.4 ms, G = 37 -> 3.56 ms,
+  // G = 74 (one round) -> 3.79 ms).  `rot` > 1 interleaves rot sub-groups inside a round (kept for experiments).
   const int sms = num_sms();
   const int pairs = sms / 2;
   auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-  int G = env_int("TNB200_CHAIN_G", pairs / max_tps);
+  int min_tps = steps[0].tiles_per_sample;
+  for (int i = 1; i < nsteps; ++i) if (steps[i].tiles_per_sample < min_tps) min_tps = steps[i].tiles_per_sample;
+  if (batch * min_tps < pairs && !env_int("TNB200_CHAIN_FORCE", 0))
+    return TNB200_ERR_UNSUPPORTED;      // too few tiles per step to hide the producer->consumer latency: launch step by step
+  int G = env_int("TNB200_CHAIN_G", (2 * pairs + min_tps - 1) / min_tps);
   if (G < 1) G = 1;
-  int rot = env_int("TNB200_CHAIN_ROT", 3);
+  int rot = env_int("TNB200_CHAIN_ROT", 1);
   if (rot < 1) rot = 1;
   std::vector<ChainSeg> segs;
   long long tile0 = 0;
