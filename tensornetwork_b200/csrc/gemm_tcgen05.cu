@@ -48,6 +48,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
   __trap();
 }
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking probe
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
@@ -1045,28 +1054,42 @@ gemm_tcgen05_chain_kernel(const __grid_constant__ ChainParams cp) {
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue (both CTAs: their own 128 rows)
+    // Publishing a tile part needs a device-scope release AFTER its stores are performed: done right after the
+    // drain it would stall the warp for the full store round trip (ncu: MEMBAR + CCTL.IVALL were the top stalls of
+    // the epilogue warps).  Instead the publication of tile i is deferred until tile i+1's accumulator is ready —
+    // by then the stores have long completed and the fence is free — or done immediately when the warp would
+    // otherwise idle (a pending publication must never wait behind a dependency: that could deadlock).
     const int q = warp & 3;
     int acc = 0; uint32_t acc_ph = 0;
     int cursor = 0;
+    uint32_t* pending = nullptr;
+    auto publish = [&]() {
+      if (pending != nullptr) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) red_release_add_u32(pending, 1u);
+        pending = nullptr;
+      }
+    };
     for (long long tile = first; tile < cp.num_tiles; tile += step) {
       ChainTile t;
       const ChainStepDev* sd = chain_decode(cp, tile, cursor, t);
       const TcParams p = sd->p;                              // per-step output description (registers / local)
       const int64_t row = (int64_t)t.mi * 2 * kBM + (int64_t)rank * kBM + q * 32 + lane;
       const int64_t n0 = (int64_t)t.ni * p.BN;
+      if (!mbar_test(tfull_bar(acc), acc_ph)) publish();     // idle anyway: publish now
       mbar_wait(tfull_bar(acc), acc_ph);
+      publish();                                             // previous tile's stores are long done: cheap
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
       epilogue_drain(p, taddr0, p.BN, t.bi, row - lane, lane, n0, epi_slab + (uint32_t)q * kSlabBytes);
       tc_fence_before();
-      __threadfence();                                       // this lane's stores are visible device-wide ...
       __syncwarp();
-      if (lane == 0) {
-        if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0);
-        red_release_add_u32(cp.done + (size_t)t.step * cp.batch + t.bi, 1u);   // ... before the tile part is published
-      }
+      if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), 0); }
+      pending = cp.done + (size_t)t.step * cp.batch + t.bi;
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
+    publish();
   }
 
   tc_fence_before();

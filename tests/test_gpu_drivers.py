@@ -223,3 +223,43 @@ def test_chained_launch_equals_stepwise(dtype, tol, monkeypatch):
     ts = [d.to_host()[b].astype(np.float64) for d in dev]
     exact = nn.contract_path(ts + [np.conj(t) for t in ts], labels, path, [])
     assert abs(out[b] - exact) <= tol * abs(exact), (dtype, b, out[b], exact)
+
+
+def test_cfg2_full_size_fp64_vs_oracle_and_scaling_property():
+  """BASELINE configs[1] at FULL size (L=64, D=512, d=2, 127 pairwise contractions): one network in fp64 against the
+  oracle's pairwise contraction along the same greedy path (<= 1e-10), then the size-independent property
+  <c psi|c psi> = c^2 <psi|psi> on the bf16 CUDA-graph path the bench times: scaling one site tensor by 2 (exact in
+  bf16) must scale every sample's result by exactly 4 — bit for bit, through the chained launch."""
+  from tensornetwork_b200 import drivers
+  be = get_backend()
+  rng = np.random.default_rng(3)
+  L, D = 64, 512
+  dims, labels = _norm_network(L, D)
+  core = [(dims[i], 2, dims[i + 1]) for i in range(L)] * 2
+  sizes = {l: s[ax] for s, labs in zip(core, labels) for ax, l in enumerate(labs)}
+  path = nn.greedy_path(labels, [], sizes)
+  assert len(path) == 127
+  kets = [rng.standard_normal(core[i]) / np.sqrt(core[i][0] * 2) for i in range(L)]
+  ref = nn.contract_path(kets + [np.conj(k) for k in kets], labels, path, [])
+  out = drivers.contract_network([be.convert_to_tensor(k) for k in kets] + [be.convert_to_tensor(np.conj(k)) for k in kets],
+                                 labels, [], path=path, backend=be)
+  assert abs(float(out.to_host()) - ref) <= 1e-10 * abs(ref)
+  # bf16, batched samples, graph + chain: exact power-of-two scaling
+  NB = 4
+  shapes = [(NB,) + s for s in core]
+  net = drivers.CompiledNetwork(be, shapes, "bfloat16", labels, [], path=path, nbatch=1,
+                                conj_aliases={L + i: i for i in range(L)})
+  dev = [be.astype(be.convert_to_tensor((rng.standard_normal((NB,) + core[i]) / np.sqrt(core[i][0] * 2)).astype(np.float32)),
+                   "bfloat16") for i in range(L)]
+  net.load(dev + [None] * L)
+  base = net().to_host().astype(np.float64).copy()
+  assert np.all(np.isfinite(base)) and np.all(base > 0)
+  for site in (0, 31, 63):
+    scaled = list(dev)
+    scaled[site] = type(dev[site])(dev[site].t * 2, dev[site].code)       # exact in bf16
+    net.load(scaled + [None] * L)
+    np.testing.assert_array_equal(net().to_host().astype(np.float64), 4.0 * base)
+  # and within bf16 tolerance of the fp64 oracle on the same (bf16-rounded) inputs, sample 0
+  ts = [d.to_host()[0].astype(np.float64) for d in dev]
+  exact = nn.contract_path(ts + [np.conj(t) for t in ts], labels, path, [])
+  assert abs(base[0] - exact) <= 0.15 * abs(exact)      # 127 bf16-rounded steps, ket/bra errors coherent
