@@ -892,6 +892,7 @@ struct ChainParams {
   uint32_t* done;                 // [nsteps][batch] completion counters (zeroed before every launch)
   long long num_tiles;
   int nsegs, batch, stages, stage_bytes;
+  int debug_no_mma;               // measurement aid (TNB200_CHAIN_NOMMA=1): stream operands, skip the MMAs
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
@@ -1044,7 +1045,7 @@ gemm_tcgen05_chain_kernel(const __grid_constant__ ChainParams cp) {
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, a_layout);
           const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, b_layout);
-          tc_mma_2sm<KIND>(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (!cp.debug_no_mma) tc_mma_2sm<KIND>(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         tc_commit_2sm(empty_bar(s));
         if (kb == num_kb - 1) tc_commit_2sm(tfull_bar(acc));
@@ -1199,6 +1200,7 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
   h->cp.steps = h->d_steps; h->cp.segs = h->d_segs; h->cp.done = h->d_done;
   h->cp.num_tiles = tile0; h->cp.nsegs = (int)segs.size(); h->cp.batch = (int)batch;
   h->cp.stages = stages; h->cp.stage_bytes = max_stage;
+  h->cp.debug_no_mma = env_int("TNB200_CHAIN_NOMMA", 0);
   h->smem = (size_t)stages * max_stage + (2 * stages + 4) * 8 + 32 + 4 * kSlabBytes + 1024;
   const long long np = tile0 < pairs ? tile0 : pairs;
   h->grid = (unsigned)(2 * np);

@@ -545,10 +545,35 @@ class CompiledNetwork:
     be = self.backend
     n_in = len(self.inputs)
     shp = plan_shapes(self._shapes, self.steps)
+    # A result whose ONLY consumer is the next step of its run needs no buffer of its own: such results
+    # alternate between two ring buffers (step s+2 starts, per sample, after step s+1 has consumed step s),
+    # so a run's intermediates are overwritten while still dirty in L2 instead of being written back to HBM.
+    import os  # pylint: disable=import-outside-toplevel
+    torch = be.torch
+    users = {}
+    for i, st in enumerate(self.steps):
+      for x in ((st[1], st[2]) if st[0] != "transpose" else (st[1],)):
+        users.setdefault(x, []).append(i)
+    ring_of = {}
+    nring = int(os.environ.get("TNB200_CHAIN_RING", "2"))
+    if nring >= 2:
+      for run in find_chains(self.steps, n_in):
+        need = 0
+        for k, sid in enumerate(run[:-1]):
+          if users.get(n_in + sid, []) == [run[k + 1]] and n_in + sid != self.res_slot:
+            need = max(need, int(np.prod(shp[n_in + sid])))
+        if need:
+          bufs = [torch.empty(need, dtype=self._tdt, device=be.device) for _ in range(nring)]
+          for k, sid in enumerate(run[:-1]):
+            if users.get(n_in + sid, []) == [run[k + 1]] and n_in + sid != self.res_slot:
+              ring_of[sid] = bufs[k % nring]
     vals = list(self.inputs)
     for i, st in enumerate(self.steps):
       if st[0] == "transpose":
         vals.append(be.transpose(vals[st[1]], st[2]))
+      elif i in ring_of:
+        n = int(np.prod(shp[n_in + i]))
+        vals.append(B200Tensor(ring_of[i][:n].view(tuple(shp[n_in + i])), code))
       else:
         vals.append(be._new(shp[n_in + i], code))  # pylint: disable=protected-access
     self._vals = vals
