@@ -77,14 +77,19 @@ class ClockSampler(threading.Thread):
     super().__init__(daemon=True)
     self.gpu = gpu_index
     self.samples = []
+    self.times = []
+    self.window = None               # (t0, t1) host time of the timed region: summary() prefers samples inside it
     self.stop_flag = False
 
   def run(self):
     # one long-running nvidia-smi in loop mode (a fresh process per sample costs ~50 ms and would see
     # one or two samples of a 100 ms timed region)
     try:
-      proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
-                               "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      import shutil  # pylint: disable=import-outside-toplevel
+      cmd = ["nvidia-smi", "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-i", str(self.gpu), "-lms", "20"]
+      if shutil.which("stdbuf"):
+        cmd = ["stdbuf", "-oL"] + cmd              # line-buffered pipe: samples arrive as they are taken
+      proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except Exception:  # pylint: disable=broad-except
       return
     try:
@@ -92,6 +97,7 @@ class ClockSampler(threading.Thread):
         f = [x.strip() for x in line.strip().split(",")]
         if len(f) >= 8:
           self.samples.append(f)
+          self.times.append(time.time())
         if self.stop_flag:
           break
     finally:
@@ -104,6 +110,11 @@ class ClockSampler(threading.Thread):
   def summary(self):
     if not self.samples:
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    allsamples = self.samples
+    if self.window is not None:
+      inside = [s for s, t in zip(self.samples, self.times) if self.window[0] <= t <= self.window[1] + 0.02]
+      if inside:
+        self.samples = inside
     sm = sorted(float(s[1]) for s in self.samples)
     reasons = []
     for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
@@ -111,7 +122,7 @@ class ClockSampler(threading.Thread):
       if any(s[col].lower().startswith("active") for s in self.samples):
         reasons.append(name)
     return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": reasons,
-            "samples": len(self.samples)}
+            "samples": len(self.samples), "samples_total": len(allsamples)}
 
 
 # ------------------------------------------------------------------------- reference arm
@@ -185,6 +196,7 @@ def main():
   ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
   ap.add_argument("--cpu-baseline-steps", type=int, default=2)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-e2e-overlap", action="store_true", help="e2e: copy and contract strictly in sequence (one compiled instance)")
   ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg1", "flagship", "cfg3", "cfg4", "cfg5", "tree32"],
                   help="cfg2 (default) is the headline line of the driver contract; the others are the remaining "
                        "SURVEY 8(d) configurations, single GPU, same JSON keys")
@@ -274,22 +286,22 @@ def main():
     torch.cuda.synchronize()
 
   # ---- device-resident timing ------------------------------------------------------
+  sampler = ClockSampler(local)      # samples every 20 ms from the warm-up on (same load as the timed region)
+  sampler.start()
   for _ in range(args.warmup):
     res = step_resident()
   barrier()
-  sampler = ClockSampler(local)
-  sampler.start()
   l0 = lib.tnb200_launch_count()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  w0 = time.time()
   e0.record()
   for _ in range(args.steps):
     res = step_resident()
   e1.record()
   barrier()
+  sampler.window = (w0, time.time())
   launches = (net.launches_per_replay * args.steps) if net is not None else (lib.tnb200_launch_count() - l0)
   ms = e0.elapsed_time(e1)
-  sampler.stop_flag = True
-  sampler.join(timeout=2)
   result_value = [float(x) for x in np.atleast_1d(res.to_host().astype(np.float64))]
 
   # ---- latency of ONE network (no sample batching): the same plan compiled for a single MPS sample
@@ -320,17 +332,57 @@ def main():
     kstats = kernel_profile(be, dev, labels, path, work, nbatch, NB, esize)
 
   # ---- end-to-end timing (host buffers) ----------------------------------------------
-  for _ in range(args.warmup):
-    step_e2e()
+  # Every step copies ITS inputs host->device (one transfer of the pinned staging arena) and reads ITS result back.
+  # Two compiled instances ping-pong: the copy of step i+1 (copy stream) overlaps the contraction of step i (compute
+  # stream); all contractions stay on one stream, in order.
+  if net is not None:
+    nets = [net]
+    if not args.no_e2e_overlap:
+      net_b = drivers.CompiledNetwork(be, shapes, {"bf16": "bfloat16", "f32": np.float32, "f64": np.float64}[args.dtype],
+                                      labels, [], path=path, nbatch=nbatch, conj_aliases=aliases)
+      for dst, src in zip(net_b.host_staging(), dev):
+        if dst is not None:
+          dst.copy_(src.t)
+      nets.append(net_b)
+    copy_s, comp_s = torch.cuda.Stream(), torch.cuda.Stream()
+    ev_in = [torch.cuda.Event() for _ in nets]
+    ev_done = [torch.cuda.Event() for _ in nets]
+    res_host = [torch.empty(max(NB, 1), dtype=tdtype).pin_memory() for _ in nets]
+
+    def run_e2e(n):
+      cur = torch.cuda.current_stream()
+      copy_s.wait_stream(cur)
+      comp_s.wait_stream(cur)
+      for i in range(n):
+        k = i % len(nets)
+        with torch.cuda.stream(copy_s):
+          if i >= len(nets):
+            copy_s.wait_event(ev_done[k])          # instance k's previous step has consumed its inputs
+          nets[k].stage()
+          ev_in[k].record(copy_s)
+        with torch.cuda.stream(comp_s):
+          comp_s.wait_event(ev_in[k])
+          out = nets[k]()
+          res_host[k].copy_(out.t.reshape(-1), non_blocking=True)     # D2H of the step's result
+          ev_done[k].record(comp_s)
+      cur.wait_stream(copy_s)
+      cur.wait_stream(comp_s)
+  else:
+    def run_e2e(n):
+      for _ in range(n):
+        step_e2e()
+  run_e2e(args.warmup)
   barrier()
   t0 = torch.cuda.Event(enable_timing=True)
   t1 = torch.cuda.Event(enable_timing=True)
   t0.record()
-  for _ in range(args.steps):
-    out = step_e2e()
+  run_e2e(args.steps)
   t1.record()
   barrier()
   ms_e2e = t0.elapsed_time(t1)
+  sampler.stop_flag = True                     # sampled from the first warm-up step to the end of the e2e region
+  sampler.join(timeout=2)
+  e2e_check = [float(x) for x in res_host[0][:4].float()] if net is not None else None
 
   if world > 1:
     tt = torch.tensor([ms, ms_e2e], device=be.device, dtype=torch.float64)
@@ -403,7 +455,9 @@ def main():
         "roofline": roof,
         "e2e": {"value": world * NB * npair * args.steps / (ms_e2e * 1e-3), "unit": "contractions/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": esize * NB,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "result_check": e2e_check,
+                "mode": "H2D of step i+1 overlapped with the contraction of step i (two compiled instances)"
+                        if (net is not None and not args.no_e2e_overlap) else "copy, contract, read back in sequence"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "result_check": result_value[:4],

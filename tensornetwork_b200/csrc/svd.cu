@@ -121,35 +121,41 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
         T e = one_<T>();
         if (mag > 1e-300) {
           e = unit_conj_phase(gpq);
-          const double tau = (aqq - app) / (2.0 * mag);
-          const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-          c = 1.0 / sqrt(1.0 + t * t);
+          // t = sign(tau) / (|tau| + sqrt(1 + tau^2)), tau = (aqq - app) / (2 mag), written with one sqrt, one
+          // division and one rsqrt (this scalar chain is the latency of every Jacobi step)
+          const double dd = aqq - app, m2 = 2.0 * mag;
+          const double t = (dd >= 0.0 ? m2 : -m2) / (fabs(dd) + sqrt(fma(dd, dd, m2 * m2)));
+          c = rsqrt(fma(t, t, 1.0));
           s = t * c;
         }
         cs[tid] = c; sn[tid] = s; ph[tid] = e; pp[tid] = p; qq[tid] = q;
       }
       __syncthreads();
-      // column rotations of G and of the accumulated eigenvector matrix
-      // columns:  x_p' = c x_p - s e x_q ,  x_q' = s x_p + c e x_q      (e = e^{-i phi})
+      // G <- J^H G J with J = the SB disjoint rotations of this step: the 2x2 block (rows p_i,q_i x columns p_j,q_j)
+      // of every (row pair, column pair) is touched by exactly one thread, so the column rotation
+      //   x_p' = c x_p - s e x_q ,  x_q' = s x_p + c e x_q            (e = e^{-i phi})
+      // and the row rotation  r_p' = c r_p - s conj(e) r_q ,  r_q' = s r_p + c conj(e) r_q  are applied back to back
+      // in registers, in place (same arithmetic, in the same order, as two separate passes — one barrier less per step)
+      {
+        const int ki = tid >> 4, kj = tid & 15;
+        const int pi = pp[ki], qi = qq[ki], pj = pp[kj], qj = qq[kj];
+        const double cjj = cs[kj], sjj = sn[kj], cii = cs[ki], sii = sn[ki];
+        const T ej = ph[kj], eic = cj(ph[ki]);
+        const T a = g[pi][pj], b = mul(ej, g[pi][qj]), c2 = g[qi][pj], d = mul(ej, g[qi][qj]);
+        const T a1 = sub(mulr(a, cjj), mulr(b, sjj)), b1 = add(mulr(a, sjj), mulr(b, cjj));
+        const T c1 = sub(mulr(c2, cjj), mulr(d, sjj)), d1 = add(mulr(c2, sjj), mulr(d, cjj));
+        const T yc = mul(eic, c1), yd = mul(eic, d1);
+        g[pi][pj] = sub(mulr(a1, cii), mulr(yc, sii)); g[qi][pj] = add(mulr(a1, sii), mulr(yc, cii));
+        g[pi][qj] = sub(mulr(b1, cii), mulr(yd, sii)); g[qi][qj] = add(mulr(b1, sii), mulr(yd, cii));
+      }
+      // accumulated eigenvector matrix: column rotations only
       for (int idx = tid; idx < SB * PB; idx += 256) {
         int k = idx / PB, i = idx % PB;
         const double c = cs[k], s = sn[k];
         const T e = ph[k];
         int p = pp[k], q = qq[k];
-        T x = g[i][p], y = mul(e, g[i][q]);
-        g[i][p] = sub(mulr(x, c), mulr(y, s)); g[i][q] = add(mulr(x, s), mulr(y, c));
-        x = rm[i][p]; y = mul(e, rm[i][q]);
+        T x = rm[i][p], y = mul(e, rm[i][q]);
         rm[i][p] = sub(mulr(x, c), mulr(y, s)); rm[i][q] = add(mulr(x, s), mulr(y, c));
-      }
-      __syncthreads();
-      // rows (J^H G):  r_p' = c r_p - s conj(e) r_q ,  r_q' = s r_p + c conj(e) r_q
-      for (int idx = tid; idx < SB * PB; idx += 256) {
-        int k = idx / PB, j = idx % PB;
-        const double c = cs[k], s = sn[k];
-        const T e = cj(ph[k]);
-        int p = pp[k], q = qq[k];
-        T x = g[p][j], y = mul(e, g[q][j]);
-        g[p][j] = sub(mulr(x, c), mulr(y, s)); g[q][j] = add(mulr(x, s), mulr(y, c));
       }
       __syncthreads();
     }

@@ -767,6 +767,11 @@ class CompiledNetwork:
         self._host_views.append(self._host_arena[off:off + n * self._esz].view(self._tdt).view(shp))
     return self._host_views
 
+  def stage(self):
+    """ONE asynchronous host->device copy of the pinned staging arena on the current stream (pair it with
+    `__call__()` on another stream + events to overlap the transfer of the next step with this step's compute)"""
+    self._arena.copy_(self._host_arena, non_blocking=True)
+
   def run_staged(self):
     """one H2D of the staging arena + graph replay"""
     self._arena.copy_(self._host_arena, non_blocking=True)
