@@ -71,7 +71,7 @@ def path_and_work(shapes, labels):
 class ClockSampler(threading.Thread):
   QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-           "clocks_event_reasons.sw_power_cap")
+           "clocks_event_reasons.sw_power_cap,timestamp")
 
   def __init__(self, gpu_index=0):
     super().__init__(daemon=True)
@@ -97,7 +97,14 @@ class ClockSampler(threading.Thread):
         f = [x.strip() for x in line.strip().split(",")]
         if len(f) >= 8:
           self.samples.append(f)
-          self.times.append(time.time())
+          t = time.time()                          # fallback: when the line was read
+          if len(f) >= 9:
+            try:                                   # nvidia-smi's own sampling time (the reader thread may lag behind)
+              import datetime  # pylint: disable=import-outside-toplevel
+              t = datetime.datetime.strptime(f[8], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:  # pylint: disable=broad-except
+              pass
+          self.times.append(t)
         if self.stop_flag:
           break
     finally:
@@ -217,8 +224,7 @@ def main():
   import torch
   import torch.distributed as dist
   if world > 1:
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "INFO"):
-      os.environ["NCCL_DEBUG"] = "WARN"           # rank 0's stdout carries exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # rank 0's stdout carries exactly one JSON line
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
   torch.cuda.set_device(local)
   import tensornetwork_b200 as tb

@@ -15,6 +15,7 @@
 //    about the order of k, and a tile's columns can be any 8 columns) so that every thread's loads and
 //    stores are 8/16-byte vectors and every warp instruction covers whole 32-byte sectors.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace tnb {
 
@@ -378,7 +379,9 @@ __global__ void __launch_bounds__(256) thin_mma_kernel(const __grid_constant__ T
 }
 
 // ------------------------------------------------------------------------------------------ host side
+static inline int thin_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static inline unsigned thin_grid_x(int64_t work_items, int64_t batch, int ctas_per_sm) {
+  ctas_per_sm = thin_env("TNB200_THIN_CPS", ctas_per_sm);      // tuning knob (CTAs per SM the grid is sized for)
   int64_t want = ((int64_t)num_sms() * ctas_per_sm + batch - 1) / batch;
   int64_t cap = (work_items + 255) / 256;
   if (want > cap) want = cap;
@@ -425,7 +428,7 @@ template <int DT, int KT, int PT>
 static int launch_mma_kp(int mode, const ThinParams& p, cudaStream_t st) {
   using T = typename DType<DT>::T;
   // registers: ~50 (16x16) .. ~190 (64x64) per thread -> 1..4 CTAs of 256 threads per SM
-  const int ctas = (KT * PT >= 8) ? 1 : (KT * PT >= 4 ? 2 : 4);
+  const int ctas = thin_env("TNB200_THIN_MMA_CPS", (KT * PT >= 8) ? 1 : (KT * PT >= 4 ? 2 : 4));
   int64_t want = ((int64_t)num_sms() * ctas + p.batch - 1) / p.batch;
   const int64_t cap = ((p.L >> 6) + 7) / 8;
   if (want > cap) want = cap;

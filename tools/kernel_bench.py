@@ -54,6 +54,34 @@ if __name__ == "__main__":
     run(be, dt, (64, 1024, 512), (64, 512, 1024), None, reps=3, batch=True)
     run(be, dt, (512, 2, 512), (512, 2, 512), [[2], [0]], reps=3)
     sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "--ramp":
+    # the thin ramp-up steps of cfg 2 (small matrix x long tensor, 74 samples): GB/s of each layout / width
+    nb = int(sys.argv[2]) if len(sys.argv) > 2 else 74
+    for k in (2, 4, 8, 16, 32, 64, 128):
+      L = 524288 // k
+      for mode in ("A", "D"):
+        if mode == "A":
+          S = tb.B200Tensor(torch.randn((nb, k, k), device=be.device).to(torch.bfloat16))
+          X = tb.B200Tensor(torch.randn((nb, k, L), device=be.device).to(torch.bfloat16))
+          f = lambda: be._contract(S, X, [2], [1], [0], [0])
+        else:
+          X = tb.B200Tensor(torch.randn((nb, L, k), device=be.device).to(torch.bfloat16))
+          S = tb.B200Tensor(torch.randn((nb, k, k), device=be.device).to(torch.bfloat16))
+          f = lambda: be._contract(X, S, [2], [1], [0], [0])
+        for _ in range(3):
+          f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+          f()
+        e1.record(); torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        byts = nb * 2.0 * (2 * k * L + k * k)
+        print(json.dumps({"ramp_k": k, "mode": mode, "kernel": be.lib.tnb200_last_kernel().decode(), "us": round(us, 1),
+                          "gbs": round(byts / us / 1e3, 1)}))
+    sys.exit(0)
   if len(sys.argv) > 1 and sys.argv[1] == "--stepab":
     # eager launches of the two bulk cfg-2 steps at NB samples (for ncu --set full captures)
     nb = int(sys.argv[2]) if len(sys.argv) > 2 else 32
