@@ -13,7 +13,7 @@ namespace tnb {
 
 int copy_strided(const tnb200_tensor_t* src, const tnb200_tensor_t* dst, int conj, cudaStream_t st);
 int tensordot_thin(int dt, const void* A, const void* B, void* C, const ModeList& mB, const ModeList& mM,
-                   const ModeList& mN, const ModeList& mK, cudaStream_t st);
+                   const ModeList& mN, const ModeList& mK, bool allow_tf32, cudaStream_t st);
 int tensordot_skinny(int dt, const void* A, const void* B, void* C, const ModeList& mB, const ModeList& mM,
                      const ModeList& mN, const ModeList& mK, cudaStream_t st);
 
@@ -415,7 +415,7 @@ extern "C" int32_t tnb200_tensordot(const tnb200_tensor_t* a, const tnb200_tenso
   if (math != (TNB200_MATH_SIMT >> 4)) {
     ModeList sK = mK;
     merge_modes(sK, 2);
-    int rc = tensordot_thin(dt, a->data, b->data, c->data, gB, gM, gN, sK, st);
+    int rc = tensordot_thin(dt, a->data, b->data, c->data, gB, gM, gN, sK, math != (TNB200_MATH_STRICT >> 4), st);
     if (rc != TNB200_ERR_UNSUPPORTED) return rc;
     rc = tensordot_skinny(dt, a->data, b->data, c->data, gB, gM, gN, sK, st);
     if (rc != TNB200_ERR_UNSUPPORTED) return rc;

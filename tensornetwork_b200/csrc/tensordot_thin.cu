@@ -378,6 +378,129 @@ __global__ void __launch_bounds__(256) thin_mma_kernel(const __grid_constant__ T
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ warp MMA, fp32 as TF32
+// Same scheme with mma.sync.m16n8k8 (tf32 inputs = the fp32 bit patterns, fp32 accumulate — the precision class of the
+// tcgen05 kind::tf32 path these shapes would otherwise take).  K = 8*KT8 in {16, 32, 64}; P <= 16*PT.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int KT8, int PT, int MODE>
+__global__ void __launch_bounds__(256) thin_mma32_kernel(const __grid_constant__ ThinParams p) {
+  constexpr int KK = 8 * KT8, PP = 16 * PT, PITCH = KK + 4;
+  __shared__ __align__(16) float sS[PP * PITCH];   // S as [p][k], zero padded rows
+  __shared__ long long cOff[PP];
+  const int64_t bb = blockIdx.y;
+  const float* Xb = (const float*)p.X + bb * p.bX;
+  const float* Sb = (const float*)p.S + bb * p.bS;
+  float* Cb = (float*)p.C + bb * p.bC;
+  for (int idx = threadIdx.x; idx < PP * KK; idx += blockDim.x) {
+    const int pp = idx / KK, k = idx % KK;
+    float v = 0.f;
+    if (pp < p.P) {
+      int64_t os, oc;
+      mode_offsets(p.mP, pp, os, oc);
+      v = Sb[os + k * p.sSk];
+      if (k == 0) cOff[pp] = oc;
+    }
+    sS[pp * PITCH + k] = v;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int64_t wstride = (int64_t)gridDim.x * (blockDim.x >> 5);
+
+  if constexpr (MODE == 0) {
+    // ---- mode A: 32 long-indices per warp block; tile column c of mma j  <->  l = l0 + 16 (c & 1) + 4 (c >> 1) + j
+    const int64_t nblk = p.L >> 5;
+    const int colbase = 16 * (g & 1) + 4 * (g >> 1);
+    for (int64_t blk = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; blk < nblk; blk += wstride) {
+      const int64_t l0 = blk << 5;
+      const float* xp = Xb + l0 + colbase;
+      uint4 x[KT8][2];
+#pragma unroll
+      for (int t = 0; t < KT8; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) x[t][h] = ldg16(xp + (int64_t)(8 * t + q + 4 * h) * p.sXk);
+#pragma unroll
+      for (int mt = 0; mt < PT; ++mt) {
+        if (16 * mt >= p.P) break;
+        float acc[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+#pragma unroll
+        for (int t = 0; t < KT8; ++t) {
+          const float* r0 = sS + (16 * mt + g) * PITCH + 8 * t + q;
+          const uint32_t a[4] = {__float_as_uint(r0[0]), __float_as_uint(r0[8 * PITCH]), __float_as_uint(r0[4]),
+                                 __float_as_uint(r0[8 * PITCH + 4])};
+          mma_tf32(acc[0], a, x[t][0].x, x[t][1].x);
+          mma_tf32(acc[1], a, x[t][0].y, x[t][1].y);
+          mma_tf32(acc[2], a, x[t][0].z, x[t][1].z);
+          mma_tf32(acc[3], a, x[t][0].w, x[t][1].w);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = 16 * mt + g + 8 * h;
+          if (row < p.P) {
+            float* cp = Cb + cOff[row] + l0 + 4 * q;
+            *reinterpret_cast<float4*>(cp) = make_float4(acc[0][2 * h], acc[1][2 * h], acc[2][2 * h], acc[3][2 * h]);
+            *reinterpret_cast<float4*>(cp + 16) = make_float4(acc[0][2 * h + 1], acc[1][2 * h + 1], acc[2][2 * h + 1], acc[3][2 * h + 1]);
+          }
+        }
+      }
+    }
+  } else {
+    // ---- mode D: X rows are the A operand; thread q owns the contiguous k-chunk [2 KT8 q, 2 KT8 (q + 1)) of a row:
+    // k-step t, slot q + 4h  <->  k = 2 KT8 q + 2 t + h.  Output column c of tile pt  <->  p = 16 (pt / 2) + 4 (c >> 1)
+    // + 2 (pt % 2) + (c & 1), so a thread's two tiles of a piece are 4 consecutive floats.
+    constexpr int NP8 = 2 * PT;
+    constexpr int RG = KT8 == 8 ? 2 : 4;                  // 16-row groups per warp block
+    const int64_t nblk = p.L / (16 * RG);
+    for (int64_t blk = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; blk < nblk; blk += wstride) {
+      const int64_t l0 = blk * (16 * RG);
+      uint32_t xa[RG][2][2 * KT8];
+#pragma unroll
+      for (int rg = 0; rg < RG; ++rg)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float* rp = Xb + (l0 + 16 * rg + 8 * h + g) * p.sXl + 2 * KT8 * q;
+#pragma unroll
+          for (int v4 = 0; v4 < KT8 / 2; ++v4) {
+            const uint4 v = ldg16(rp + 4 * v4);
+            xa[rg][h][4 * v4] = v.x; xa[rg][h][4 * v4 + 1] = v.y; xa[rg][h][4 * v4 + 2] = v.z; xa[rg][h][4 * v4 + 3] = v.w;
+          }
+        }
+#pragma unroll
+      for (int rg = 0; rg < RG; ++rg) {
+        float acc[NP8][4];
+#pragma unroll
+        for (int pt = 0; pt < NP8; ++pt) { acc[pt][0] = acc[pt][1] = acc[pt][2] = acc[pt][3] = 0.f; }
+#pragma unroll
+        for (int t = 0; t < KT8; ++t) {
+          const uint32_t a[4] = {xa[rg][0][2 * t], xa[rg][1][2 * t], xa[rg][0][2 * t + 1], xa[rg][1][2 * t + 1]};
+#pragma unroll
+          for (int pt = 0; pt < NP8; ++pt) {
+            const int pcol = (pt >> 1) * 16 + 4 * (g >> 1) + 2 * (pt & 1) + (g & 1);
+            const float2 b = *reinterpret_cast<const float2*>(sS + pcol * PITCH + 2 * KT8 * q + 2 * t);
+            mma_tf32(acc[pt], a, __float_as_uint(b.x), __float_as_uint(b.y));
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float* cp = Cb + (l0 + 16 * rg + 8 * h + g) * p.sCl + 4 * q;
+#pragma unroll
+          for (int piece = 0; piece < NP8 / 2; ++piece)
+            *reinterpret_cast<float4*>(cp + 16 * piece) =
+                make_float4(acc[2 * piece][2 * h], acc[2 * piece][2 * h + 1], acc[2 * piece + 1][2 * h], acc[2 * piece + 1][2 * h + 1]);
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static inline int thin_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static inline unsigned thin_grid_x(int64_t work_items, int64_t batch, int ctas_per_sm) {
@@ -452,12 +575,38 @@ static int launch_mma(int mode, const ThinParams& p, cudaStream_t st) {
   return TNB200_ERR_UNSUPPORTED;
 }
 
+template <int KT8, int PT>
+static int launch_mma32_kp(int mode, const ThinParams& p, cudaStream_t st) {
+  const int ctas = thin_env("TNB200_THIN_MMA_CPS", (KT8 * PT >= 16) ? 2 : 4);
+  const int64_t nblk = mode == 0 ? (p.L >> 5) : p.L / (16 * (KT8 == 8 ? 2 : 4));
+  int64_t want = ((int64_t)num_sms() * ctas + p.batch - 1) / p.batch;
+  const int64_t cap = (nblk + 7) / 8;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  dim3 grid((unsigned)want, (unsigned)p.batch);
+  if (mode == 0) thin_mma32_kernel<KT8, PT, 0><<<grid, 256, 0, st>>>(p);
+  else thin_mma32_kernel<KT8, PT, 1><<<grid, 256, 0, st>>>(p);
+  TNB_LAUNCH_CHECK();
+  count_launch();
+  set_kernel_name(mode == 0 ? "thin_mma_tf32_a" : "thin_mma_tf32_d");
+  return 0;
+}
+static int launch_mma32(int mode, const ThinParams& p, cudaStream_t st) {
+  const int kt = p.K / 8, pt = (p.P + 15) / 16 <= 1 ? 1 : ((p.P + 15) / 16 <= 2 ? 2 : 4);
+#define TNB_THIN_M32(KT8, PT) if (kt == KT8 && pt == PT) return launch_mma32_kp<KT8, PT>(mode, p, st);
+  TNB_THIN_M32(2, 1) TNB_THIN_M32(2, 2) TNB_THIN_M32(2, 4)
+  TNB_THIN_M32(4, 1) TNB_THIN_M32(4, 2) TNB_THIN_M32(4, 4)
+  TNB_THIN_M32(8, 1) TNB_THIN_M32(8, 2) TNB_THIN_M32(8, 4)
+#undef TNB_THIN_M32
+  return TNB200_ERR_UNSUPPORTED;
+}
+
 static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 // Planner entry (mode-list conventions of tensordot.cu: mB s0 A, s1 B, s2 C; mM s0 A, s1 C; mN s0 B, s1 C;
 // mK s0 A, s1 B; all lists merged).  Returns TNB200_ERR_UNSUPPORTED when the shape / layout is not thin.
 int tensordot_thin(int dt, const void* A, const void* B, void* C, const ModeList& mB, const ModeList& mM,
-                   const ModeList& mN, const ModeList& mK, cudaStream_t st) {
+                   const ModeList& mN, const ModeList& mK, bool allow_tf32, cudaStream_t st) {
   if (dt != TNB200_F32 && dt != TNB200_F16 && dt != TNB200_BF16) return TNB200_ERR_UNSUPPORTED;
   if (mB.n > 1 || mK.n != 1) return TNB200_ERR_UNSUPPORTED;
   const int64_t M = mM.total(), N = mN.total(), K = mK.total(), batch = mB.total();
@@ -518,6 +667,16 @@ int tensordot_thin(int dt, const void* A, const void* B, void* C, const ModeList
       if (p.sXl % 8 || p.sCl % 8) return TNB200_ERR_UNSUPPORTED;
     }
     return dt == TNB200_F16 ? launch_mma<TNB200_F16>(mode, p, st) : launch_mma<TNB200_BF16>(mode, p, st);
+  }
+  // ---- warp-MMA family, fp32 as TF32 (not under TNB200_MATH_STRICT: the planner routes strict fp32 elsewhere)
+  if (dt == TNB200_F32 && allow_tf32 && (K == 16 || K == 32 || K == 64) && p.P > 8) {
+    if (mode == 0) {
+      if (p.L % 32) return TNB200_ERR_UNSUPPORTED;
+    } else {
+      if (!(p.P == 16 || p.P == 32 || p.P == 64)) return TNB200_ERR_UNSUPPORTED;
+      if (p.sXl % 4 || p.sCl % 4 || p.L % 64) return TNB200_ERR_UNSUPPORTED;
+    }
+    return launch_mma32(mode, p, st);
   }
   return TNB200_ERR_UNSUPPORTED;
 }

@@ -185,25 +185,26 @@ def test_thin_simt_both_layouts(dtype, kp):
   assert e < tol, (dtype, kp, "D", kern, e)
 
 
-@pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16", "float32"])
 @pytest.mark.parametrize("kp", [(16, 16), (32, 32), (64, 64), (16, 64), (64, 16), (32, 64), (64, 32), (16, 32), (32, 16)])
 def test_thin_mma_both_layouts(dtype, kp):
   be = get_backend()
   rng = np.random.default_rng(32)
   k, p = kp
   nb, L = 5, 16384
+  sfx = "_tf32" if dtype == "float32" else ""
   # mode A with a two-leg S (site tensor (p/2, 2, k)) and batch
   S, s = _mk(be, rng, (nb, p // 2, 2, k), dtype)
   X, x = _mk(be, rng, (nb, k, 2, L // 2), dtype)
   out = be._contract(S, X, [3], [1], [0], [0])
-  assert be.lib.tnb200_last_kernel().decode() == "thin_mma_a"
+  assert be.lib.tnb200_last_kernel().decode() == "thin_mma" + sfx + "_a"
   e = rel_err(out.to_host(), np.einsum("bpqk,bkxl->bpqxl", s, x))
   assert e < TOLS[dtype], (dtype, kp, "A", e)
   # mode D with a two-leg S (site tensor (k, 2, p/2))
   X, x = _mk(be, rng, (nb, L, k), dtype)
   S, s = _mk(be, rng, (nb, k, 2, p // 2), dtype)
   out = be._contract(X, S, [2], [1], [0], [0])
-  assert be.lib.tnb200_last_kernel().decode() == "thin_mma_d"
+  assert be.lib.tnb200_last_kernel().decode() == "thin_mma" + sfx + "_d"
   e = rel_err(out.to_host(), np.einsum("blk,bkqp->blqp", x, s))
   assert e < TOLS[dtype], (dtype, kp, "D", e)
 
@@ -217,3 +218,21 @@ def test_thin_mma_masked_rows_and_unbatched():
   out = be.tensordot(be.transpose(S), X, 1)
   assert be.lib.tnb200_last_kernel().decode() == "thin_mma_a"
   assert rel_err(out.to_host(), s.T @ x) < TOLS["bfloat16"]
+
+
+def test_thin_fp32_strict_mode_stays_fp32():
+  """TNB200_MATH_STRICT: the thin fp32 shapes must not take the TF32 warp-MMA kernel (true fp32 accuracy 2e-5)."""
+  from tensornetwork_b200 import _lib as L
+  be = get_backend()
+  rng = np.random.default_rng(34)
+  S, s = _mk(be, rng, (3, 32, 32), "float32")
+  X, x = _mk(be, rng, (3, 32, 32768), "float32")
+  old = be.math_mode
+  be.math_mode = L.MATH_STRICT
+  try:
+    out = be._contract(S, X, [2], [1], [0], [0])
+    kern = be.lib.tnb200_last_kernel().decode()
+  finally:
+    be.math_mode = old
+  assert "tf32" not in kern and not kern.startswith("tcgen05"), kern
+  assert rel_err(out.to_host(), np.einsum("bpk,bkl->bpl", s, x)) < 2e-5
