@@ -67,6 +67,29 @@ def path_and_work(shapes, labels):
   return path, steps
 
 
+# ------------------------------------------------------------------------------- output
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+  """The driver reads ONE JSON line from stdout.  Libraries may write to file descriptor 1 directly (NCCL prints its
+  version banner there): point fd 1 at stderr for the life of the process and keep the real stdout for emit()."""
+  global _REAL_STDOUT
+  if _REAL_STDOUT is None:
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+  data = (json.dumps(line) + "\n").encode()
+  if _REAL_STDOUT is None:
+    sys.stdout.write(data.decode())
+    sys.stdout.flush()
+  else:
+    os.write(_REAL_STDOUT, data)
+
+
 # ------------------------------------------------------------------------------- clocks
 class ClockSampler(threading.Thread):
   QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -133,6 +156,27 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------- reference arm
+def tune_blas_threads(fn):
+  """The reference's numpy backend is only as fast as its BLAS threading: on a many-core host OpenBLAS with ALL
+  threads is slower on these mid-size GEMMs than with a few dozen.  Time `fn` (one network) under several thread
+  limits and return (best_limit, context-manager factory) so the baseline is the reference at its best."""
+  cores = os.cpu_count() or 1
+  try:
+    from threadpoolctl import threadpool_limits  # pylint: disable=import-outside-toplevel
+  except ImportError:
+    return cores, None
+  best, best_t = cores, None
+  for n in sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}):
+    with threadpool_limits(limits=n):
+      fn()
+      t0 = time.perf_counter()
+      fn()
+      dt = time.perf_counter() - t0
+    if best_t is None or dt < best_t:
+      best, best_t = n, dt
+  return best, threadpool_limits
+
+
 def run_reference(args, rank, world):
   """The reference's CPU algorithm for the same workload: numpy backend restated in oracle/
   (tensordot = numpy_backend.py:35-54 -> np.tensordot/OpenBLAS, path = greedy, pairwise loop
@@ -157,15 +201,19 @@ def run_reference(args, rank, world):
       path = nn.greedy_path(labels, [], sizes)   # the reference searches the path on every call
       out = nn.contract_path(ts, labels, path, [])
     return out
-  for _ in range(args.warmup):
-    step()
-  t0 = time.perf_counter()
-  for _ in range(args.steps):
-    res = step()
-  dt = time.perf_counter() - t0
+  path0 = nn.greedy_path(labels, [], sizes)
+  threads, limiter = tune_blas_threads(lambda: nn.contract_path(nets[0], labels, path0, []))
+  import contextlib  # pylint: disable=import-outside-toplevel
+  with (limiter(limits=threads) if limiter else contextlib.nullcontext()):
+    for _ in range(args.warmup):
+      step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+      res = step()
+    dt = time.perf_counter() - t0
   npair = len(tensors) - 1
   val = nsamp * npair * args.steps / dt
-  cores = os.cpu_count()
+  cores = threads
   line = {
       "impl": "reference", "metric": "pairwise contractions/s", "value": val, "unit": "contractions/s",
       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -173,12 +221,13 @@ def run_reference(args, rank, world):
       "dtype": "f32" if np_dtype == np.float32 else "f64", "data": "synthetic",
       "config": workload_config(args, 1),
       "cpu_baseline": {"value": val, "unit": "contractions/s", "cores": cores, "kind": "port",
-                       "sample": "%d networks per step x %d steps (127 pairwise each), numpy %s, OpenBLAS threads=all"
-                                 % (nsamp, args.steps, np.dtype(np_dtype).name)},
+                       "sample": "%d networks per step x %d steps (127 pairwise each), numpy %s, BLAS threads = %d (fastest of "
+                                 "8/16/32/64/all on this host; %d logical cores)"
+                                 % (nsamp, args.steps, np.dtype(np_dtype).name, threads, os.cpu_count())},
       "e2e": {"value": val, "unit": "contractions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
       "result_check": float(np.real(res)),
   }
-  print(json.dumps(line))
+  emit(line)
 
 
 def workload_config(args, world):
@@ -208,6 +257,7 @@ def main():
                   help="cfg2 (default) is the headline line of the driver contract; the others are the remaining "
                        "SURVEY 8(d) configurations, single GPU, same JSON keys")
   args = ap.parse_args()
+  quiet_stdout()
   args.warmup = max(args.warmup, 3) if args.impl == "cuda_b200" else max(args.warmup, 1)
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -337,6 +387,8 @@ def main():
   else:
     kstats = kernel_profile(be, dev, labels, path, work, nbatch, NB, esize)
 
+  sampler.stop_flag = True      # clocks sampled every 20 ms over warm-up + timed region + per-kernel pass (all under the
+  sampler.join(timeout=2)       # same compute load); the PCIe-bound e2e section below is not part of the sample
   # ---- end-to-end timing (host buffers) ----------------------------------------------
   # Every step copies ITS inputs host->device (one transfer of the pinned staging arena) and reads ITS result back.
   # Two compiled instances ping-pong: the copy of step i+1 (copy stream) overlaps the contraction of step i (compute
@@ -386,8 +438,6 @@ def main():
   t1.record()
   barrier()
   ms_e2e = t0.elapsed_time(t1)
-  sampler.stop_flag = True                     # sampled from the first warm-up step to the end of the e2e region
-  sampler.join(timeout=2)
   e2e_check = [float(x) for x in res_host[0][:4].float()] if net is not None else None
 
   if world > 1:
@@ -471,7 +521,7 @@ def main():
     }
     if not args.no_cpu_baseline and world == 1:
       line["cpu_baseline"] = cpu_baseline(args)
-    print(json.dumps(line))
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 
@@ -524,14 +574,18 @@ def cpu_baseline(args):
   labels = norm_labels(L_SITES)
   sizes = {l: t.shape[ax] for t, labs in zip(tensors, labels) for ax, l in enumerate(labs)}
   path = nn.greedy_path(labels, [], sizes)
-  nn.contract_path(tensors, labels, path, [])
-  t0 = time.perf_counter()
+  threads, limiter = tune_blas_threads(lambda: nn.contract_path(tensors, labels, path, []))
+  import contextlib  # pylint: disable=import-outside-toplevel
   n = args.cpu_baseline_steps
-  for _ in range(n):
+  with (limiter(limits=threads) if limiter else contextlib.nullcontext()):
     nn.contract_path(tensors, labels, path, [])
-  dt = time.perf_counter() - t0
-  return {"value": (len(tensors) - 1) * n / dt, "unit": "contractions/s", "cores": os.cpu_count(), "kind": "port",
-          "sample": "%d full networks (127 pairwise each) in numpy %s, all host threads" % (n, np.dtype(np_dtype).name)}
+    t0 = time.perf_counter()
+    for _ in range(n):
+      nn.contract_path(tensors, labels, path, [])
+    dt = time.perf_counter() - t0
+  return {"value": (len(tensors) - 1) * n / dt, "unit": "contractions/s", "cores": threads, "kind": "port",
+          "sample": "%d full networks (127 pairwise each) in numpy %s, BLAS threads = %d (fastest of 8/16/32/64/all; "
+                    "%d logical cores)" % (n, np.dtype(np_dtype).name, threads, os.cpu_count())}
 
 
 # ------------------------------------------------------------------ the other SURVEY 8(d) configurations
@@ -781,7 +835,7 @@ def run_config(args):
   sampler.stop_flag = True
   sampler.join(timeout=2)
   line["clocks"] = sampler.summary()
-  print(json.dumps(line))
+  emit(line)
 
 
 if __name__ == "__main__":
