@@ -101,6 +101,7 @@ class ClockSampler(threading.Thread):
     self.gpu = gpu_index
     self.samples = []
     self.times = []
+    self.read_times = []
     self.window = None               # (t0, t1) host time of the timed region: summary() prefers samples inside it
     self.stop_flag = False
 
@@ -121,6 +122,7 @@ class ClockSampler(threading.Thread):
         if len(f) >= 8:
           self.samples.append(f)
           t = time.time()                          # fallback: when the line was read
+          self.read_times.append(t)
           if len(f) >= 9:
             try:                                   # nvidia-smi's own sampling time (the reader thread may lag behind)
               import datetime  # pylint: disable=import-outside-toplevel
@@ -142,9 +144,11 @@ class ClockSampler(threading.Thread):
       return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
     allsamples = self.samples
     if self.window is not None:
-      inside = [s for s, t in zip(self.samples, self.times) if self.window[0] <= t <= self.window[1] + 0.02]
-      if inside:
-        self.samples = inside
+      for stamps in (self.times, self.read_times):      # nvidia-smi's own sampling time first, then arrival time
+        inside = [s for s, t in zip(allsamples, stamps) if self.window[0] <= t <= self.window[1] + 0.05]
+        if inside:
+          self.samples = inside
+          break
     sm = sorted(float(s[1]) for s in self.samples)
     reasons = []
     for name, col in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
@@ -281,6 +285,8 @@ def main():
   from tensornetwork_b200 import drivers, _lib
   be = tb.get_backend()
   lib = be.lib
+  sampler = ClockSampler(local)      # started early (nvidia-smi needs ~1 s to produce its first sample); only samples
+  sampler.start()                    # inside the window [first warm-up step, end of the per-kernel pass] are reported
 
   code = {"bf16": _lib.BF16, "f32": _lib.F32, "f64": _lib.F64}[args.dtype]
   tdtype = {"bf16": torch.bfloat16, "f32": torch.float32, "f64": torch.float64}[args.dtype]
@@ -342,20 +348,18 @@ def main():
     torch.cuda.synchronize()
 
   # ---- device-resident timing ------------------------------------------------------
-  sampler = ClockSampler(local)      # samples every 20 ms from the warm-up on (same load as the timed region)
-  sampler.start()
+  win0 = time.time()
   for _ in range(args.warmup):
     res = step_resident()
   barrier()
   l0 = lib.tnb200_launch_count()
   e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  w0 = time.time()
   e0.record()
   for _ in range(args.steps):
     res = step_resident()
   e1.record()
   barrier()
-  sampler.window = (w0, time.time())
+  sampler.window = (win0, time.time())
   launches = (net.launches_per_replay * args.steps) if net is not None else (lib.tnb200_launch_count() - l0)
   ms = e0.elapsed_time(e1)
   result_value = [float(x) for x in np.atleast_1d(res.to_host().astype(np.float64))]
@@ -387,8 +391,10 @@ def main():
   else:
     kstats = kernel_profile(be, dev, labels, path, work, nbatch, NB, esize)
 
-  sampler.stop_flag = True      # clocks sampled every 20 ms over warm-up + timed region + per-kernel pass (all under the
-  sampler.join(timeout=2)       # same compute load); the PCIe-bound e2e section below is not part of the sample
+  torch.cuda.synchronize()
+  sampler.window = (win0, time.time())   # warm-up + timed region + single-network + per-kernel pass: all compute load;
+  sampler.stop_flag = True               # the PCIe-bound e2e section below is not part of the clock sample
+  sampler.join(timeout=2)
   # ---- end-to-end timing (host buffers) ----------------------------------------------
   # Every step copies ITS inputs host->device (one transfer of the pinned staging arena) and reads ITS result back.
   # Two compiled instances ping-pong: the copy of step i+1 (copy stream) overlaps the contraction of step i (compute
