@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "cplx.cuh"
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace tnb {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(256) svd_gram_kernel(const T* __restrict__ W, 
 // Diagonalise the PB x PB Gram matrix of each pair; write the rotation, clear G for the next round,
 // record the largest relative off-diagonal seen BEFORE rotating (sweep convergence measure).
 template <typename T>
-__global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __restrict__ Rout, unsigned int* conv, double tol_inner) {
+__global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __restrict__ Rout, unsigned int* conv, double tol_inner, int max_inner) {
   __shared__ T g[PB][PB + 1];
   __shared__ T rm[PB][PB + 1];
   __shared__ double cs[SB], sn[SB];
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
     gg[idx] = zero_<T>();
   }
   __syncthreads();
-  for (int sweep = 0; sweep < 10; ++sweep) {
+  for (int sweep = 0; sweep < max_inner; ++sweep) {
     // relative off-diagonal measure
     float loc = 0.f;
     for (int idx = tid; idx < PB * PB; idx += 256) {
@@ -289,7 +290,11 @@ static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tn
 
   const double eps = 2.220446049250313e-16;
   const double tol = 4.0 * sqrt((double)R) * eps;
-  const double tol_inner = 1e-15;
+  // inner (Gram) eigen-solver: tolerance / sweep cap (env knobs for experiments; the outer criterion is unchanged)
+  const char* e_tol = getenv("TNB200_SVD_INNER_TOL");
+  const char* e_sw = getenv("TNB200_SVD_INNER_SWEEPS");
+  const double tol_inner = e_tol ? atof(e_tol) : 1e-15;
+  const int max_inner = e_sw ? atoi(e_sw) : 10;
   int rsplit = (4 * num_sms() + npairs - 1) / npairs;
   int max_split = (int)((R + 4 * RT - 1) / (4 * RT));
   if (rsplit > max_split) rsplit = max_split;
@@ -303,7 +308,7 @@ static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tn
     TNB_CHECK_CUDA(cudaMemsetAsync(conv, 0, sizeof(unsigned int), st));
     for (int r = 0; r < rounds; ++r) {
       svd_gram_kernel<T><<<dim3(npairs, rsplit), 256, 0, st>>>(W, R, nb, r, G, rsplit);
-      svd_eig_kernel<T><<<npairs, 256, 0, st>>>(G, Rm, conv, tol_inner);
+      svd_eig_kernel<T><<<npairs, 256, 0, st>>>(G, Rm, conv, tol_inner, max_inner);
       svd_update_kernel<T><<<dim3(npairs, usplit_w), 256, 0, st>>>(W, R, nb, r, Rm);
       svd_update_kernel<T><<<dim3(npairs, usplit_v), 256, 0, st>>>(V, Cp, nb, r, Rm);
     }
