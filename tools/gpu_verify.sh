@@ -12,3 +12,9 @@ for f in ("gpurun_out/BENCH_default.json","gpurun_out/BENCH_reference.json"):
   print("   e2e", d.get("e2e")); print("   cpu", d.get("cpu_baseline")); print("   clocks", d.get("clocks"), "single", d.get("single_network"))
   r=d.get("roofline") or {}; print("   roof", {k:r.get(k) for k in ("bound","achieved","peak","unit","frac","traffic","kernel","kernel_share_of_step_time")})
 PY
+( time timeout 900 python bench.py --dtype f64 --steps 3 --no-cpu-baseline > gpurun_out/BENCH_f64.json 2> gpurun_out/BENCH_f64.err ) 2>&1 | tail -3; tail -2 gpurun_out/BENCH_f64.err
+python - <<PY
+import json
+d=json.loads(open("gpurun_out/BENCH_f64.json").read().strip().splitlines()[-1])
+print("f64", {k:d.get(k) for k in ("value","ms_per_step")}, d["e2e"])
+PY
