@@ -21,9 +21,13 @@ namespace tnb {
 
 int copy_strided(const tnb200_tensor_t* src, const tnb200_tensor_t* dst, int conj, cudaStream_t st);
 
-constexpr int SB = 16;        // block width
-constexpr int PB = 2 * SB;    // columns handled per pair
-constexpr int RT = 64;        // rows per shared-memory tile
+// Block width SB (columns per block; a pair rotates PB = 2 SB columns) is a template parameter: 16 is the default,
+// 32 an experiment (see svd_dispatch): every round streams W and V through HBM once, and doubling the block width
+// halves the number of rounds per sweep, but the Gram eigenproblem grows to 64 x 64 (still one CTA).
+template <int SB> struct Geo {
+  static constexpr int PB = 2 * SB;
+  static constexpr int RT = SB == 16 ? 64 : 32;     // rows per shared-memory tile of the gram / update kernels
+};
 
 // round-robin tournament on nb (even) players: pair p of round r
 __device__ __forceinline__ void rr_pair(int nb, int r, int p, int& i, int& j) {
@@ -32,10 +36,12 @@ __device__ __forceinline__ void rr_pair(int nb, int r, int p, int& i, int& j) {
   else { i = (r + p) % m; j = (r - p + m) % m; }
   if (i > j) { int t = i; i = j; j = t; }
 }
+template <int SB>
 __device__ __forceinline__ int pair_col(int bi, int bj, int c) { return c < SB ? bi * SB + c : bj * SB + (c - SB); }
 
-template <typename T>
+template <typename T, int SB>
 __global__ void __launch_bounds__(256) svd_gram_kernel(const T* __restrict__ W, int64_t R, int nb, int round, T* __restrict__ G, int rsplit) {
+  constexpr int PB = Geo<SB>::PB, RT = Geo<SB>::RT, TPT = PB / 16;   // 16 x 16 threads, TPT x TPT outputs each
   __shared__ T tile[PB][RT + 1];
   const int pair = blockIdx.x, chunk = blockIdx.y;
   int bi, bj;
@@ -43,46 +49,59 @@ __global__ void __launch_bounds__(256) svd_gram_kernel(const T* __restrict__ W, 
   const int64_t rows_per = ((R + rsplit - 1) / rsplit + RT - 1) / RT * RT;
   const int64_t r0 = chunk * rows_per, r1 = min(R, r0 + rows_per);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  T acc[2][2];
-  acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = zero_<T>();
+  T acc[TPT][TPT];
+#pragma unroll
+  for (int a = 0; a < TPT; ++a)
+#pragma unroll
+    for (int b = 0; b < TPT; ++b) acc[a][b] = zero_<T>();
   for (int64_t rb = r0; rb < r1; rb += RT) {
     for (int idx = threadIdx.x; idx < PB * RT; idx += 256) {
       int c = idx / RT, rr = idx % RT;
       int64_t row = rb + rr;
-      tile[c][rr] = row < r1 ? W[(int64_t)pair_col(bi, bj, c) * R + row] : zero_<T>();
+      tile[c][rr] = row < r1 ? W[(int64_t)pair_col<SB>(bi, bj, c) * R + row] : zero_<T>();
     }
     __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
     for (int rr = 0; rr < RT; ++rr) {
-      T a0 = cj(tile[ty * 2][rr]), a1 = cj(tile[ty * 2 + 1][rr]), b0 = tile[tx * 2][rr], b1 = tile[tx * 2 + 1][rr];
-      fmacc(acc[0][0], a0, b0); fmacc(acc[0][1], a0, b1); fmacc(acc[1][0], a1, b0); fmacc(acc[1][1], a1, b1);
+      T av[TPT], bv[TPT];
+#pragma unroll
+      for (int a = 0; a < TPT; ++a) { av[a] = cj(tile[ty * TPT + a][rr]); bv[a] = tile[tx * TPT + a][rr]; }
+#pragma unroll
+      for (int a = 0; a < TPT; ++a)
+#pragma unroll
+        for (int b = 0; b < TPT; ++b) fmacc(acc[a][b], av[a], bv[b]);
     }
     __syncthreads();
   }
   T* g = G + (int64_t)pair * PB * PB;     // G = W^H W (Hermitian)
 #pragma unroll
-  for (int a = 0; a < 2; ++a)
+  for (int a = 0; a < TPT; ++a)
 #pragma unroll
-    for (int b = 0; b < 2; ++b) atomic_add(&g[(ty * 2 + a) * PB + tx * 2 + b], acc[a][b]);
+    for (int b = 0; b < TPT; ++b) atomic_add(&g[(ty * TPT + a) * PB + tx * TPT + b], acc[a][b]);
 }
 
 // Diagonalise the PB x PB Gram matrix of each pair; write the rotation, clear G for the next round,
 // record the largest relative off-diagonal seen BEFORE rotating (sweep convergence measure).
-template <typename T>
+// Dynamic shared memory: g[PB][PB+1], rm[PB][PB+1] (T), then cs[SB], sn[SB] (double), ph[SB] (T), pp[SB], qq[SB] (int).
+template <typename T, int SB>
 __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __restrict__ Rout, unsigned int* conv, double tol_inner, int max_inner) {
-  __shared__ T g[PB][PB + 1];
-  __shared__ T rm[PB][PB + 1];
-  __shared__ double cs[SB], sn[SB];
-  __shared__ T ph[SB];          // e^{-i phi} of the pivot (real case: its sign is folded into t instead)
-  __shared__ int pp[SB], qq[SB];
+  constexpr int PB = Geo<SB>::PB, LD = PB + 1;
+  extern __shared__ __align__(16) unsigned char eig_smem[];
+  T* g = reinterpret_cast<T*>(eig_smem);
+  T* rm = g + PB * LD;
+  double* cs = reinterpret_cast<double*>(rm + PB * LD);
+  double* sn = cs + SB;
+  T* ph = reinterpret_cast<T*>(sn + SB);          // e^{-i phi} of the pivot (real case: its sign is folded into t instead)
+  int* pp = reinterpret_cast<int*>(ph + SB);
+  int* qq = pp + SB;
   __shared__ float red[8];
   __shared__ float offmax;
   const int pair = blockIdx.x, tid = threadIdx.x;
   T* gg = G + (int64_t)pair * PB * PB;
   for (int idx = tid; idx < PB * PB; idx += 256) {
     int i = idx / PB, j = idx % PB;
-    g[i][j] = gg[idx];
-    rm[i][j] = i == j ? one_<T>() : zero_<T>();
+    g[i * LD + j] = gg[idx];
+    rm[i * LD + j] = i == j ? one_<T>() : zero_<T>();
     gg[idx] = zero_<T>();
   }
   __syncthreads();
@@ -92,8 +111,8 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
     for (int idx = tid; idx < PB * PB; idx += 256) {
       int i = idx / PB, j = idx % PB;
       if (i < j) {
-        double d = re_(g[i][i]) * re_(g[j][j]);
-        if (d > 0.0) { float v = (float)(sqrt(ab2(g[i][j])) / sqrt(d)); loc = fmaxf(loc, v); }
+        double d = re_(g[i * LD + i]) * re_(g[j * LD + j]);
+        if (d > 0.0) { float v = (float)(sqrt(ab2(g[i * LD + j])) / sqrt(d)); loc = fmaxf(loc, v); }
       }
     }
     for (int o = 16; o > 0; o >>= 1) loc = fmaxf(loc, __shfl_xor_sync(0xffffffffu, loc, o));
@@ -115,8 +134,8 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
         if (p > q) { int t = p; p = q; q = t; }
         // Hermitian 2x2 [[a, g], [conj g, b]], g = |g| e^{i phi}: rotate (x_p, e^{-i phi} x_q) by the
         // real Jacobi angle of [[a, |g|], [|g|, b]]
-        const T gpq = g[p][q];
-        const double app = re_(g[p][p]), aqq = re_(g[q][q]);
+        const T gpq = g[p * LD + q];
+        const double app = re_(g[p * LD + p]), aqq = re_(g[q * LD + q]);
         const double mag = sqrt(ab2(gpq));
         double c = 1.0, s = 0.0;
         T e = one_<T>();
@@ -137,17 +156,17 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
       //   x_p' = c x_p - s e x_q ,  x_q' = s x_p + c e x_q            (e = e^{-i phi})
       // and the row rotation  r_p' = c r_p - s conj(e) r_q ,  r_q' = s r_p + c conj(e) r_q  are applied back to back
       // in registers, in place (same arithmetic, in the same order, as two separate passes — one barrier less per step)
-      {
-        const int ki = tid >> 4, kj = tid & 15;
+      for (int blk = tid; blk < SB * SB; blk += 256) {
+        const int ki = blk / SB, kj = blk % SB;
         const int pi = pp[ki], qi = qq[ki], pj = pp[kj], qj = qq[kj];
         const double cjj = cs[kj], sjj = sn[kj], cii = cs[ki], sii = sn[ki];
         const T ej = ph[kj], eic = cj(ph[ki]);
-        const T a = g[pi][pj], b = mul(ej, g[pi][qj]), c2 = g[qi][pj], d = mul(ej, g[qi][qj]);
+        const T a = g[pi * LD + pj], b = mul(ej, g[pi * LD + qj]), c2 = g[qi * LD + pj], d = mul(ej, g[qi * LD + qj]);
         const T a1 = sub(mulr(a, cjj), mulr(b, sjj)), b1 = add(mulr(a, sjj), mulr(b, cjj));
         const T c1 = sub(mulr(c2, cjj), mulr(d, sjj)), d1 = add(mulr(c2, sjj), mulr(d, cjj));
         const T yc = mul(eic, c1), yd = mul(eic, d1);
-        g[pi][pj] = sub(mulr(a1, cii), mulr(yc, sii)); g[qi][pj] = add(mulr(a1, sii), mulr(yc, cii));
-        g[pi][qj] = sub(mulr(b1, cii), mulr(yd, sii)); g[qi][qj] = add(mulr(b1, sii), mulr(yd, cii));
+        g[pi * LD + pj] = sub(mulr(a1, cii), mulr(yc, sii)); g[qi * LD + pj] = add(mulr(a1, sii), mulr(yc, cii));
+        g[pi * LD + qj] = sub(mulr(b1, cii), mulr(yd, sii)); g[qi * LD + qj] = add(mulr(b1, sii), mulr(yd, cii));
       }
       // accumulated eigenvector matrix: column rotations only
       for (int idx = tid; idx < SB * PB; idx += 256) {
@@ -155,19 +174,25 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
         const double c = cs[k], s = sn[k];
         const T e = ph[k];
         int p = pp[k], q = qq[k];
-        T x = rm[i][p], y = mul(e, rm[i][q]);
-        rm[i][p] = sub(mulr(x, c), mulr(y, s)); rm[i][q] = add(mulr(x, s), mulr(y, c));
+        T x = rm[i * LD + p], y = mul(e, rm[i * LD + q]);
+        rm[i * LD + p] = sub(mulr(x, c), mulr(y, s)); rm[i * LD + q] = add(mulr(x, s), mulr(y, c));
       }
       __syncthreads();
     }
   }
   T* ro = Rout + (int64_t)pair * PB * PB;
-  for (int idx = tid; idx < PB * PB; idx += 256) ro[idx] = rm[idx / PB][idx % PB];
+  for (int idx = tid; idx < PB * PB; idx += 256) ro[idx] = rm[(idx / PB) * LD + idx % PB];
+}
+template <typename T, int SB>
+static size_t eig_smem_bytes() {
+  constexpr int PB = Geo<SB>::PB;
+  return 2 * sizeof(T) * PB * (PB + 1) + SB * (2 * sizeof(double) + sizeof(T) + 2 * sizeof(int)) + 16;
 }
 
 // X[:, pair columns] <- X[:, pair columns] * R   (X = W or V; column-contiguous with `rows` rows)
-template <typename T>
+template <typename T, int SB>
 __global__ void __launch_bounds__(256) svd_update_kernel(T* __restrict__ X, int64_t rows, int nb, int round, const T* __restrict__ Rm) {
+  constexpr int PB = Geo<SB>::PB, RT = Geo<SB>::RT, NCG = 256 / RT, CPT = PB / NCG;   // CPT = 8 outputs per thread
   __shared__ T tile[PB][RT];     // read as tile[k][row]: consecutive threads -> consecutive rows (no padding needed)
   __shared__ T rs[PB][PB];       // read as broadcast
   const int pair = blockIdx.x;
@@ -175,28 +200,28 @@ __global__ void __launch_bounds__(256) svd_update_kernel(T* __restrict__ X, int6
   rr_pair(nb, round, pair, bi, bj);
   const T* rg = Rm + (int64_t)pair * PB * PB;
   for (int idx = threadIdx.x; idx < PB * PB; idx += 256) rs[idx / PB][idx % PB] = rg[idx];
-  const int rr = threadIdx.x & (RT - 1), cg = threadIdx.x / RT;   // 64 rows x 4 column groups of 8
+  const int rr = threadIdx.x & (RT - 1), cg = threadIdx.x / RT;   // RT rows x NCG column groups of CPT
   for (int64_t rb = (int64_t)blockIdx.y * RT; rb < rows; rb += (int64_t)gridDim.y * RT) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < PB * RT; idx += 256) {
       int c = idx / RT, r2 = idx % RT;
       int64_t row = rb + r2;
-      tile[c][r2] = row < rows ? X[(int64_t)pair_col(bi, bj, c) * rows + row] : zero_<T>();
+      tile[c][r2] = row < rows ? X[(int64_t)pair_col<SB>(bi, bj, c) * rows + row] : zero_<T>();
     }
     __syncthreads();
-    T out[8];
+    T out[CPT];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) out[c] = zero_<T>();
+    for (int c = 0; c < CPT; ++c) out[c] = zero_<T>();
 #pragma unroll 8
     for (int k = 0; k < PB; ++k) {
       T x = tile[k][rr];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) fmacc(out[c], x, rs[k][cg * 8 + c]);
+      for (int c = 0; c < CPT; ++c) fmacc(out[c], x, rs[k][cg * CPT + c]);
     }
     int64_t row = rb + rr;
     if (row < rows) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) X[(int64_t)pair_col(bi, bj, cg * 8 + c) * rows + row] = out[c];
+      for (int c = 0; c < CPT; ++c) X[(int64_t)pair_col<SB>(bi, bj, cg * CPT + c) * rows + row] = out[c];
     }
   }
 }
@@ -255,9 +280,10 @@ __global__ void svd_eye_kernel(T* V, int Cp) {
   if (idx < (int64_t)Cp * Cp) V[idx] = (idx / Cp == idx % Cp) ? one_<T>() : zero_<T>();
 }
 
-template <typename T>
+template <typename T, int SB>
 static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tnb200_tensor_t* s, const tnb200_tensor_t* vh,
                     int32_t* info_dev, cudaStream_t st) {
+  constexpr int PB = Geo<SB>::PB, RT = Geo<SB>::RT;
   const int64_t m = a->shape[0], n = a->shape[1];
   const bool tall = m >= n;
   const int64_t R = tall ? m : n;
@@ -301,16 +327,24 @@ static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tn
   if (rsplit < 1) rsplit = 1;
   int usplit_w = (int)((R + RT - 1) / RT); if (usplit_w > rsplit * 4) usplit_w = rsplit * 4;
   int usplit_v = (Cp + RT - 1) / RT; if (usplit_v > rsplit * 4) usplit_v = rsplit * 4;
+  const size_t eig_bytes = eig_smem_bytes<T, SB>();
+  {
+    static bool attr_done = false;      // per (T, SB) instantiation
+    if (!attr_done) {
+      TNB_CHECK_CUDA(cudaFuncSetAttribute(svd_eig_kernel<T, SB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eig_bytes));
+      attr_done = true;
+    }
+  }
   const int max_sweeps = 40;
   int sweeps = 0, converged = 0;
   unsigned int h_conv = 0;
   for (int sw = 0; sw < max_sweeps; ++sw) {
     TNB_CHECK_CUDA(cudaMemsetAsync(conv, 0, sizeof(unsigned int), st));
     for (int r = 0; r < rounds; ++r) {
-      svd_gram_kernel<T><<<dim3(npairs, rsplit), 256, 0, st>>>(W, R, nb, r, G, rsplit);
-      svd_eig_kernel<T><<<npairs, 256, 0, st>>>(G, Rm, conv, tol_inner, max_inner);
-      svd_update_kernel<T><<<dim3(npairs, usplit_w), 256, 0, st>>>(W, R, nb, r, Rm);
-      svd_update_kernel<T><<<dim3(npairs, usplit_v), 256, 0, st>>>(V, Cp, nb, r, Rm);
+      svd_gram_kernel<T, SB><<<dim3(npairs, rsplit), 256, 0, st>>>(W, R, nb, r, G, rsplit);
+      svd_eig_kernel<T, SB><<<npairs, 256, eig_bytes, st>>>(G, Rm, conv, tol_inner, max_inner);
+      svd_update_kernel<T, SB><<<dim3(npairs, usplit_w), 256, 0, st>>>(W, R, nb, r, Rm);
+      svd_update_kernel<T, SB><<<dim3(npairs, usplit_v), 256, 0, st>>>(V, Cp, nb, r, Rm);
     }
     count_launch(4 * rounds);
     TNB_LAUNCH_CHECK();
@@ -361,6 +395,20 @@ __global__ void svd_trunc_kernel(const T* __restrict__ s, int64_t n, int64_t str
 
 using namespace tnb;
 
+// Block width: 16.  The 32-wide variant (half the rounds per sweep, i.e. half the HBM traffic of the gram / update
+// kernels) is kept for real dtypes behind TNB200_SVD_SB=32, but it is SLOWER on B200 — measured 2048^2: 0.57 s vs
+// 0.37 s, 4096^2: 2.20 s vs 2.06 s, same sweep counts — because the 64 x 64 Gram eigenproblem (63 dependent Jacobi
+// steps per inner sweep in one CTA) then dominates every round.
+static int svd_dispatch(bool cplx, const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tnb200_tensor_t* s, const tnb200_tensor_t* vh,
+                        int32_t* info_dev, cudaStream_t st) {
+  if (cplx) return svd_real<zd, 16>(a, u, s, vh, info_dev, st);
+  const int64_t cn = a->shape[0] < a->shape[1] ? a->shape[0] : a->shape[1];
+  int sb = 16;
+  (void)cn;
+  if (const char* e = getenv("TNB200_SVD_SB")) { const int v = atoi(e); if (v == 16 || v == 32) sb = v; }
+  return sb == 32 ? svd_real<double, 32>(a, u, s, vh, info_dev, st) : svd_real<double, 16>(a, u, s, vh, info_dev, st);
+}
+
 extern "C" int32_t tnb200_svd(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tnb200_tensor_t* s, const tnb200_tensor_t* vh,
                               int32_t* info_dev, void* stream) {
   TNB_REQUIRE(valid_tensor(a) && valid_tensor(u) && valid_tensor(s) && valid_tensor(vh), TNB200_ERR_INVALID, "svd: invalid tensor descriptor");
@@ -372,8 +420,8 @@ extern "C" int32_t tnb200_svd(const tnb200_tensor_t* a, const tnb200_tensor_t* u
   TNB_REQUIRE(m < (1LL << 31) && n < (1LL << 31), TNB200_ERR_UNSUPPORTED, "svd: matrix too large");
   cudaStream_t st = (cudaStream_t)stream;
   set_kernel_name("svd_block_jacobi");
-  if (a->dtype == TNB200_F64) { TNB_REQUIRE(s->dtype == TNB200_F64, TNB200_ERR_DTYPE, "svd: s must be f64"); return svd_real<double>(a, u, s, vh, info_dev, st); }
-  if (a->dtype == TNB200_C128) { TNB_REQUIRE(s->dtype == TNB200_F64, TNB200_ERR_DTYPE, "svd: s must be f64"); return svd_real<zd>(a, u, s, vh, info_dev, st); }
+  if (a->dtype == TNB200_F64) { TNB_REQUIRE(s->dtype == TNB200_F64, TNB200_ERR_DTYPE, "svd: s must be f64"); return svd_dispatch(false, a, u, s, vh, info_dev, st); }
+  if (a->dtype == TNB200_C128) { TNB_REQUIRE(s->dtype == TNB200_F64, TNB200_ERR_DTYPE, "svd: s must be f64"); return svd_dispatch(true, a, u, s, vh, info_dev, st); }
   if (a->dtype == TNB200_F32 || a->dtype == TNB200_C64) {
     // single precision input: iterate in double (hundreds of accumulated plane rotations cost ~1e-5
     // relative accuracy in fp32, LAPACK's sgesdd delivers ~1e-6), then round the factors back.
@@ -394,7 +442,7 @@ extern "C" int32_t tnb200_svd(const tnb200_tensor_t* a, const tnb200_tensor_t* u
     };
     tnb200_tensor_t ta = mk(da, wide_dt, m, n, 2), tu = mk(du, wide_dt, m, r, 2), ts = mk(ds, TNB200_F64, r, 1, 1), tv = mk(dv, wide_dt, r, n, 2);
     if ((rc = copy_strided(a, &ta, 0, st))) return rc;
-    rc = cplx ? svd_real<zd>(&ta, &tu, &ts, &tv, info_dev, st) : svd_real<double>(&ta, &tu, &ts, &tv, info_dev, st);
+    rc = svd_dispatch(cplx, &ta, &tu, &ts, &tv, info_dev, st);
     if (rc == 0) rc = copy_strided(&tu, u, 0, st);
     if (rc == 0) rc = copy_strided(&ts, s, 0, st);
     if (rc == 0) rc = copy_strided(&tv, vh, 0, st);
