@@ -9,6 +9,8 @@ __device__ __forceinline__ double cj(double a) { return a; }
 __device__ __forceinline__ zd cj(zd a) { return zd{a.x, -a.y}; }
 __device__ __forceinline__ double ab2(double a) { return a * a; }
 __device__ __forceinline__ double ab2(zd a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ double mag_(double a) { return fabs(a); }          // |a| without the sqrt(a*a) round trip
+__device__ __forceinline__ double mag_(zd a) { return sqrt(a.x * a.x + a.y * a.y); }
 __device__ __forceinline__ double re_(double a) { return a; }
 __device__ __forceinline__ double re_(zd a) { return a.x; }
 __device__ __forceinline__ double mul(double a, double b) { return a * b; }

@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
       int i = idx / PB, j = idx % PB;
       if (i < j) {
         double d = re_(g[i * LD + i]) * re_(g[j * LD + j]);
-        if (d > 0.0) { float v = (float)(sqrt(ab2(g[i * LD + j])) / sqrt(d)); loc = fmaxf(loc, v); }
+        if (d > 0.0) { float v = (float)(ab2(g[i * LD + j]) / d); loc = fmaxf(loc, v); }     // squared; root taken once below
       }
     }
     for (int o = 16; o > 0; o >>= 1) loc = fmaxf(loc, __shfl_xor_sync(0xffffffffu, loc, o));
@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
     if (tid == 0) {
       float m = 0.f;
       for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]);
+      m = sqrtf(m);
       offmax = m;
       if (sweep == 0) atomicMax(conv, __float_as_uint(m));
     }
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(256) svd_eig_kernel(T* __restrict__ G, T* __re
         // real Jacobi angle of [[a, |g|], [|g|, b]]
         const T gpq = g[p * LD + q];
         const double app = re_(g[p * LD + p]), aqq = re_(g[q * LD + q]);
-        const double mag = sqrt(ab2(gpq));
+        const double mag = mag_(gpq);
         double c = 1.0, s = 0.0;
         T e = one_<T>();
         if (mag > 1e-300) {

@@ -1,3 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_split.py tests/test_gpu_blocksparse.py -x -q -m gpu 2>&1 | tail -4
-echo "== SB=32 (default for >= 512)"; timeout 300 python tools/kernel_bench.py --svd 1024 2048 4096 2>&1 | tail -3 | cut -c1-250
-echo "== SB=16"; TNB200_SVD_SB=16 timeout 300 python tools/kernel_bench.py --svd 2048 4096 2>&1 | tail -2 | cut -c1-250
+timeout 900 python -m pytest tests/test_gpu_split.py tests/test_gpu_blocksparse.py tests/test_gpu_drivers.py -x -q -m gpu 2>&1 | tail -4
+timeout 300 python tools/kernel_bench.py --svd 1024 2048 4096 2>&1 | tail -3 | cut -c1-250
