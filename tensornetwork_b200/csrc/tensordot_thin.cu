@@ -607,7 +607,7 @@ static inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 // mK s0 A, s1 B; all lists merged).  Returns TNB200_ERR_UNSUPPORTED when the shape / layout is not thin.
 int tensordot_thin(int dt, const void* A, const void* B, void* C, const ModeList& mB, const ModeList& mM,
                    const ModeList& mN, const ModeList& mK, bool allow_tf32, cudaStream_t st) {
-  if (dt != TNB200_F32 && dt != TNB200_F16 && dt != TNB200_BF16) return TNB200_ERR_UNSUPPORTED;
+  if (dt != TNB200_F64 && dt != TNB200_F32 && dt != TNB200_F16 && dt != TNB200_BF16) return TNB200_ERR_UNSUPPORTED;
   if (mB.n > 1 || mK.n != 1) return TNB200_ERR_UNSUPPORTED;
   const int64_t M = mM.total(), N = mN.total(), K = mK.total(), batch = mB.total();
   if (K > 64 || batch > 65535) return TNB200_ERR_UNSUPPORTED;
@@ -655,6 +655,7 @@ int tensordot_thin(int dt, const void* A, const void* B, void* C, const ModeList
       if (!((K == 2 || K == 4 || K == 8) && (p.P == 2 || p.P == 4 || p.P == 8))) return TNB200_ERR_UNSUPPORTED;
     }
     switch (dt) {
+      case TNB200_F64: return launch_simt<TNB200_F64>(mode, p, st);
       case TNB200_F32: return launch_simt<TNB200_F32>(mode, p, st);
       case TNB200_F16: return launch_simt<TNB200_F16>(mode, p, st);
       default: return launch_simt<TNB200_BF16>(mode, p, st);

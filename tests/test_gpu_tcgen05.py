@@ -152,14 +152,14 @@ def test_swap_ab_tiny_m(dtype):
 
 # ------------------------------------------------------------------------------------------------
 # thin contractions (tensordot_thin.cu): small matrix x long tensor, the ramp-up steps of the cfg-2 path
-@pytest.mark.parametrize("dtype", ["bfloat16", "float16", "float32"])
+@pytest.mark.parametrize("dtype", ["bfloat16", "float16", "float32", "float64"])
 @pytest.mark.parametrize("kp", [(2, 2), (4, 4), (8, 8), (4, 8), (8, 2), (3, 5)])
 def test_thin_simt_both_layouts(dtype, kp):
   be = get_backend()
   rng = np.random.default_rng(31)
   k, p = kp
   nb, L = 3, 32768
-  tol = TOLS[dtype] if dtype != "float32" else 2e-5
+  tol = {"float32": 2e-5, "float64": 1e-12}.get(dtype) or TOLS[dtype]
   # mode A: S[b, p1, 2, k] . X[b, k, (2, 2, L/4)] -> C[b, p1, 2, 2, 2, L/4]  (many-leg operands, merged by the planner)
   if p % 2 == 0:
     S, s = _mk(be, rng, (nb, p // 2, 2, k), dtype)
