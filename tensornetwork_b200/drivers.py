@@ -557,16 +557,22 @@ class CompiledNetwork:
     ring_of = {}
     nring = int(os.environ.get("TNB200_CHAIN_RING", "2"))
     if nring >= 2:
+      # Ring slots are shared ONLY between results of identical shape (so sample b occupies the same region in
+      # every step that uses the slot) and are handed out round-robin per shape: a slot written by step s is
+      # next written by a step s' >= s + 2, which (per sample, through the run's read-after-write counters)
+      # cannot start before step s + 1 — the only reader of step s — has finished that sample.  Results of
+      # different per-sample extents never alias (the cfg 2 ramp boundary [256,2,512] -> [512,2,512]).
       for run in find_chains(self.steps, n_in):
-        need = 0
+        rings, count = {}, {}
         for k, sid in enumerate(run[:-1]):
           if users.get(n_in + sid, []) == [run[k + 1]] and n_in + sid != self.res_slot:
-            need = max(need, int(np.prod(shp[n_in + sid])))
-        if need:
-          bufs = [torch.empty(need, dtype=self._tdt, device=be.device) for _ in range(nring)]
-          for k, sid in enumerate(run[:-1]):
-            if users.get(n_in + sid, []) == [run[k + 1]] and n_in + sid != self.res_slot:
-              ring_of[sid] = bufs[k % nring]
+            key = tuple(shp[n_in + sid])
+            if key not in rings:
+              need = int(np.prod(key))
+              rings[key] = [torch.empty(need, dtype=self._tdt, device=be.device) for _ in range(nring)]
+              count[key] = 0
+            ring_of[sid] = rings[key][count[key] % nring]
+            count[key] += 1
     vals = list(self.inputs)
     for i, st in enumerate(self.steps):
       if st[0] == "transpose":
@@ -580,6 +586,10 @@ class CompiledNetwork:
     chain_of = {}
     self.chains = []
     pending = find_chains(self.steps, n_in)
+    if code == L.F32 and be.math_mode in (L.MATH_STRICT, L.MATH_SIMT):
+      pending = []            # the chained kernel computes fp32 as TF32: strict fp32 stays on per-step launches
+    if be.math_mode == L.MATH_SIMT:
+      pending = []
     while pending:
       run = pending.pop(0)
       if len(run) < 2:

@@ -1,0 +1,86 @@
+"""Row N1: the reference's own callers, UNMODIFIED, on backend="cuda_b200" with the real kernels.
+
+The reference package is the pip-installed copy under baseline/_ref (tools/install_ref.sh), imported
+through baseline/refenv.py.  Every case of tests/ref_cases.py is run with backend="numpy" (the
+reference's own numpy backend) and backend="cuda_b200" in the same process, on the same seeded
+inputs, and compared (fp64: <= 1e-10 of the result scale; integers exact)."""
+import numpy as np
+import pytest
+import ref_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _backend(tn):
+  import tensornetwork_b200 as tb
+  from tensornetwork_b200 import backend as tbb
+  from tensornetwork.backends import abstract_backend, backend_factory
+  assert tb.registered and tbb.HAVE_TENSORNETWORK
+  be = backend_factory.get_backend("cuda_b200")
+  assert isinstance(be, abstract_backend.AbstractBackend) and be.name == "cuda_b200"
+  assert backend_factory.get_backend("cuda_b200") is be
+  return be
+
+
+@pytest.mark.parametrize("name,fn,tol", ref_cases.CASES, ids=[c[0] for c in ref_cases.CASES])
+def test_reference_caller(tn, name, fn, tol):
+  be = _backend(tn)
+  n0 = be.lib.tnb200_launch_count()
+  got = fn(tn, "cuda_b200")
+  launches = be.lib.tnb200_launch_count() - n0
+  ref = fn(tn, "numpy")
+  ref_cases.compare(name, got, ref, tol)
+  assert launches > 0, "no libtnb200 kernel ran for " + name
+
+
+def test_results_live_on_the_device(tn):
+  from tensornetwork_b200 import B200Tensor
+  be = _backend(tn)
+  a = tn.Node(np.ones((3, 4)), backend="cuda_b200")
+  b = tn.Node(np.ones((4, 5)), backend="cuda_b200")
+  a[1] ^ b[0]
+  c = a @ b
+  assert isinstance(c.tensor, B200Tensor) and c.tensor.t.is_cuda
+  assert c.backend is be
+  tn.set_default_backend("cuda_b200")
+  try:
+    assert tn.Node(np.ones(3)).backend.name == "cuda_b200"
+  finally:
+    tn.set_default_backend("numpy")
+
+
+def test_reference_error_conventions(tn):
+  be = _backend(tn)
+  with pytest.raises(TypeError):
+    be.convert_to_tensor([1, 2])
+  with pytest.raises(ValueError):
+    be.tensordot(be.convert_to_tensor(np.ones((2, 3))), be.convert_to_tensor(np.ones((4, 5))), [[1], [0]])
+  a = tn.Node(np.ones((2, 2)), backend="cuda_b200")
+  b = tn.Node(np.ones((2, 2)), backend="numpy")
+  with pytest.raises(ValueError):
+    a[0] ^ b[0]
+    tn.contract_between(a, b)
+
+
+def test_reference_greedy_mps_norm_D64_float32_and_complex(tn):
+  """A larger <psi|psi> through contractors.greedy (path_contractors.py:87-90): the per-pair loop
+  reaches the tcgen05 / DMMA / thin kernels rather than only the SIMT fallback.  float32 is checked
+  twice: strict (fp32 FMA, 1e-4 after 23 chained contractions) and the tensor-core TF32 mode, whose
+  2^-11 operand rounding accumulates over the chain (stated tolerance 2e-2)."""
+  from tensornetwork_b200 import _lib as L
+  be = _backend(tn)
+  rng = np.random.default_rng(21)
+  for dtype, mode, tol in ((np.float64, L.MATH_DEFAULT, 1e-10), (np.float32, L.MATH_STRICT, 1e-4),
+                           (np.float32, L.MATH_DEFAULT, 2e-2), (np.complex128, L.MATH_DEFAULT, 1e-10)):
+    kets = ref_cases.mps_kets(rng, 12, 64, np.float64)
+    if np.issubdtype(dtype, np.complexfloating):
+      kets = [k + 1j * rng.standard_normal(k.shape) / np.sqrt(k.shape[0]) for k in kets]
+    kets = [k.astype(dtype) for k in kets]
+    old = be.math_mode
+    be.math_mode = mode
+    try:
+      got = np.asarray(tn.contractors.greedy(ref_cases._mps_norm_nodes(tn, "cuda_b200", kets)).tensor)
+    finally:
+      be.math_mode = old
+    ref = np.asarray(tn.contractors.greedy(ref_cases._mps_norm_nodes(tn, "numpy", kets)).tensor)
+    assert abs(got - ref) <= tol * abs(ref), (dtype, mode, got, ref)
