@@ -306,6 +306,7 @@ def main():
                        "SURVEY 8(d) configurations, single GPU, same JSON keys")
   ap.add_argument("--sub", action="store_true", help="internal: this process measures a sub-record of another bench line "
                   "(no nested sub-records, single BLAS thread setting for the CPU leg)")
+  ap.add_argument("--no-strong-scaling", action="store_true", help="N > 1: skip the one-network strong-scaling sub-record")
   ap.add_argument("--no-subrecords", action="store_true", help="skip the by_dtype / configs sub-records of the default line")
   args = ap.parse_args()
   quiet_stdout()
@@ -446,6 +447,7 @@ def main():
   # Every step copies ITS inputs host->device (one transfer of the pinned staging arena) and reads ITS result back.
   # Two compiled instances ping-pong: the copy of step i+1 (copy stream) overlaps the contraction of step i (compute
   # stream); all contractions stay on one stream, in order.
+  net_b = None
   if net is not None:
     nets = [net]
     if not args.no_e2e_overlap:
@@ -497,10 +499,23 @@ def main():
   ms_e2e = t0.elapsed_time(t1)
   e2e_check = [float(x) for x in res_host[0][:4].float()] if net is not None else None
 
+  e2e_mode = ("H2D of step i+1 overlapped with the contraction of step i (two compiled instances)"
+              if (net is not None and len(nets) > 1) else "copy, contract, read back in sequence")
+  strong = None
   if world > 1:
     tt = torch.tensor([ms, ms_e2e], device=be.device, dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(tt[0]), float(tt[1])
+    if not args.no_strong_scaling:
+      # free the weak-scaling instances first (the tree network needs ~10 GB per rank)
+      net = kets = dev = nets = net_b = host = res = None
+      import gc  # pylint: disable=import-outside-toplevel
+      gc.collect()
+      torch.cuda.empty_cache()
+      try:
+        strong = strong_scaling_record(be, rank, world, dist, max(3, min(args.steps, 10)))
+      except Exception as exc:  # pylint: disable=broad-except
+        strong = {"error": "%s: %s" % (type(exc).__name__, str(exc).splitlines()[0] if str(exc) else "")}
 
   if rank == 0:
     peaks = {}
@@ -570,20 +585,19 @@ def main():
         "e2e": {"value": world * NB * npair * args.steps / (ms_e2e * 1e-3), "unit": "contractions/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": esize * NB,
                 "ms_per_step": ms_e2e / args.steps, "result_check": e2e_check,
-                "mode": "H2D of step i+1 overlapped with the contraction of step i (two compiled instances)"
-                        if (net is not None and len(nets) > 1) else "copy, contract, read back in sequence"},
+                "mode": e2e_mode},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "result_check": result_value[:4],
         "single_network": single,
     }
+    if strong is not None:
+      line["strong_scaling"] = strong
     if not args.no_cpu_baseline and world == 1:
       line["cpu_baseline"] = cpu_baseline(args)
     if world == 1 and not args.sub and not args.no_subrecords and args.config == "cfg2":
       # release this process's device memory first: the sub-records run in fresh processes on the same GPU
-      del net, kets, dev
-      if 'nets' in dir():
-        del nets
+      net = kets = dev = nets = net_b = host = res = None
       import gc  # pylint: disable=import-outside-toplevel
       gc.collect()
       torch.cuda.empty_cache()
@@ -591,6 +605,106 @@ def main():
     emit(line)
   if world > 1:
     dist.destroy_process_group()
+
+
+def ttn_network(dims=None):
+  """<T|T> of a binary tree tensor network: root -> 2 -> 4 -> 8 leaves (15 nodes) + a cap on the root's top leg = 16 ket
+  nodes, 16 conj bra nodes, closed (scalar).  The heavy work sits at the 8 leaf groups (bond b3 between a leaf and its
+  parent), the joins above are small: the contraction tree fans out 8 ways.  -> (labels, sizes, shapes)"""
+  d = {"top": 4, "cap": 4, "b1": 16, "b2": 64, "b3": 1024, "p": 16}
+  d.update(dims or {})
+  lk, lb, sizes = [], [], {}
+  bond = lambda tag, i: "%s%d" % (tag, i)
+  for i in range(15):
+    for tag, L in (("k", lk), ("b", lb)):
+      if i == 0:
+        L.append([tag + "top", bond(tag, 1), bond(tag, 2)])
+      elif i < 7:
+        L.append([bond(tag, i), bond(tag, 2 * i + 1), bond(tag, 2 * i + 2)])
+      else:
+        L.append([bond(tag, i), "p%da" % i, "p%db" % i])
+  for tag, L in (("k", lk), ("b", lb)):
+    L.append([tag + "top", "cap"])
+    sizes[tag + "top"] = d["top"]
+    for i in range(1, 15):
+      sizes[bond(tag, i)] = d["b1" if i < 3 else ("b2" if i < 7 else "b3")]
+  for i in range(7, 15):
+    sizes["p%da" % i] = sizes["p%db" % i] = d["p"]
+  sizes["cap"] = d["cap"]
+  labels = lk + lb
+  return labels, sizes, [tuple(sizes[l] for l in labs) for labs in labels], d
+
+
+def strong_scaling_record(be, rank, world, dist, steps, b3=None):
+  """ONE 32-node closed network (ttn_network, fp64) contracted on `world` GPUs by parallel.ShardedNetwork against the same
+  network on one GPU (CompiledNetwork graph replay, measured on every rank at the same time; rank 0's time is reported).
+  Device-timed, max over ranks.  Parity: against the numpy oracle on rank 0's host (fp64, 1e-10)."""
+  import torch
+  from tensornetwork_b200 import drivers, parallel
+  labels, sizes, shapes, dims = ttn_network({"b3": b3} if b3 else None)
+  path = drivers.greedy_path(labels, [], sizes)
+  n_ket = len(labels) // 2
+  kets = []
+  for i in range(n_ket):
+    t = be.randn(shapes[i], np.float64, seed=700 + i)
+    t *= 1.0 / np.sqrt(float(np.prod(shapes[i][1:])))
+    kets.append(t)
+  dev = kets + list(kets)                      # bra = conj(ket); real data
+  single = drivers.CompiledNetwork(be, shapes, np.float64, labels, [], path=path, conj_aliases={n_ket + i: i for i in range(n_ket)})
+  single.load(dev)
+  sh = parallel.ShardedNetwork(be, shapes, np.float64, labels, path, rank, world)
+  sh.load(dev)
+
+  def timed(fn):
+    for _ in range(3):
+      fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    return e0.elapsed_time(e1) / steps, out
+  ms1, out1 = timed(single)
+  msn, (outn, root_rank) = timed(sh.run)
+  tt = torch.tensor([ms1, msn], device=be.device, dtype=torch.float64)
+  dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+  ms1_max, msn_max = float(tt[0]), float(tt[1])
+  res = torch.zeros(2, device=be.device, dtype=torch.float64)
+  if rank == root_rank:
+    res[0] = outn.t.reshape(-1)[0]
+  if rank == 0:
+    res[1] = out1.t.reshape(-1)[0]
+  dist.all_reduce(res, op=dist.ReduceOp.SUM)
+  moved = torch.tensor([float(sh.p2p_bytes)], device=be.device, dtype=torch.float64)
+  dist.all_reduce(moved, op=dist.ReduceOp.SUM)
+  if rank != 0:
+    return None
+  from oracle import np_network as nn          # checker only (untimed)
+  host = [k.to_host() for k in kets]
+  ref = float(nn.contract_path(host + [np.conj(h) for h in host], labels, path, []))
+  flops = sh.step_flops
+  heavy = [f for f in flops if f >= 1e9]
+  return {
+      "network": "<T|T> of a 16-node binary tree tensor network (32 tensors, closed): bonds top=%d b1=%d b2=%d b3=%d, leaf legs %dx%d; "
+                 "greedy path, %d pairwise steps, %d of them >= 1 GFLOP (%.1f-%.1f GFLOP each)"
+                 % (dims["top"], dims["b1"], dims["b2"], dims["b3"], dims["p"], dims["p"], len(path), len(heavy), min(heavy) / 1e9, max(heavy) / 1e9),
+      "dtype": "f64", "total_gflop": sum(flops) / 1e9,
+      "ms_1gpu": ms1_max, "ms_sharded": msn_max, "n_gpus": world, "speedup": ms1_max / msn_max,
+      "bound_total_over_critical": sh.info["total"] / sh.info["critical"],
+      "bound_lpt_balance": sh.info["total"] / max(sh.info["per_rank"]),
+      "per_rank_gflop": [x / 1e9 for x in sh.info["per_rank"]],
+      "p2p_transfers": len(sh.transfers), "p2p_bytes_total": float(moved[0]) / 2.0,
+      "executor": "per rank: local subtrees as CUDA-graph replays (CompiledNetwork), steps above the cut eager; subtree results sent "
+                  "once by NCCL isend into receives posted up front; no collective on the data path",
+      "result_sharded": float(res[0]), "result_1gpu": float(res[1]), "result_oracle_fp64": ref,
+      "parity_rel_err": abs(float(res[0]) - ref) / abs(ref), "parity_ok": bool(abs(float(res[0]) - ref) <= 1e-10 * abs(ref)),
+      "tflops_1gpu": sum(flops) / ms1_max / 1e9, "tflops_sharded": sum(flops) / msn_max / 1e9,
+  }
 
 
 def _run_sub(extra, timeout=240):

@@ -11,6 +11,13 @@ from .tensor import B200Tensor, bfloat16
 
 __version__ = "0.1.0"
 registered = _backend.register()
+registered_symmetric = False
+if registered:
+  try:
+    from . import symmetric as _symmetric
+    registered_symmetric = _symmetric.register() is not None   # "symmetric_b200": the reference's SymmetricBackend, hot ops on the device
+  except Exception:  # pylint: disable=broad-except
+    registered_symmetric = False
 
 
 def get_backend():

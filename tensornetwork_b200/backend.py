@@ -77,6 +77,9 @@ class CudaB200Backend(_Base):
     self._on_cuda = self.device.type == "cuda"
     self.math_mode = L.MATH_DEFAULT
     self._seed = 0x5EED
+    self._jit_cache = {}
+    self.jit_graphs = os.environ.get("TNB200_JIT", "1") != "0"      # jit(): CUDA-graph capture (0 = identity, like numpy's)
+    self.jit_stats = {"eager": 0, "captures": 0, "replays": 0, "capture_failures": 0}
     if _INSTANCE is None:
       _INSTANCE = self
 
@@ -528,8 +531,21 @@ class CudaB200Backend(_Base):
     return np.finfo(T.code_to_np(code)).eps
 
   def jit(self, fun, *args, **kwargs):
-    """numpy_backend.py:600-601 — identity (graph capture is opt-in: see graph.py)."""
-    return fun
+    """abstract_backend.py:798 (numpy's is the identity, numpy_backend.py:600-601): returns a `jit.JitFunction` that
+    captures `fun` in a CUDA graph on the second call per (static args, shapes) key and replays it afterwards — this is
+    how `tn.ncon` (ncon_interface.py:654-660) and the DMRG `ncon`s reach graph replay without any change to the caller.
+    One JitFunction per (fun, static_argnums): `tn.jit`'s wrapper asks for a new one on every call (decorators.py:64-69)."""
+    from . import jit as _jit  # pylint: disable=import-outside-toplevel
+    static = kwargs.get("static_argnums", ())
+    static = (static,) if isinstance(static, int) else tuple(static or ())
+    key = (fun, static)
+    try:
+      jf = self._jit_cache.get(key)
+    except TypeError:
+      return fun
+    if jf is None:
+      jf = self._jit_cache[key] = _jit.JitFunction(self, fun, static)
+    return jf
 
   def serialize_tensor(self, tensor):
     import io  # pylint: disable=import-outside-toplevel

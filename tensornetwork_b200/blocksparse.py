@@ -48,17 +48,51 @@ def _signed(ix):
   return -ix.charges if ix.flow else ix.charges
 
 
+def _fused_dense(indices, mod):
+  """fused (signed) charge of every state of the product space of `indices`, row-major"""
+  fused = np.zeros(1, dtype=np.int64)
+  for ix in indices:
+    fused = np.add.outer(fused, _signed(ix)).ravel()
+  return np.mod(fused, mod) if mod else fused
+
+
 def _fused_allowed(indices):
-  """flat row-major positions (stored order) whose fused charge is the identity."""
+  """flat row-major positions (stored order) whose fused charge is the identity, ascending.
+
+  The dense index space (prod of all leg dimensions: 10^8 for the reference tutorial's (100,101,102,103) legs) is never
+  enumerated: the legs are cut into a left and a right group of balanced size, each group's fused charges are enumerated
+  (sqrt of the dense size), the right states are bucketed by charge (stable), and every left state l pairs with the bucket
+  of charge -q_l: position = l * |right| + r.  O(|left| + |right| + nnz)."""
   if not indices:
     return np.zeros(1, dtype=np.int64)
   mod = indices[0].modulus
-  fused = _signed(indices[0])
-  for ix in indices[1:]:
-    fused = np.add.outer(fused, _signed(ix)).ravel()
-  if mod:
-    fused = np.mod(fused, mod)
-  return np.nonzero(fused == 0)[0].astype(np.int64)
+  dims = [ix.dim for ix in indices]
+  total = 1
+  for d in dims:
+    total *= d
+  best, k, left = None, 1, 1
+  for i in range(1, len(dims) + 1):
+    left *= dims[i - 1]
+    cost = max(left, total // max(left, 1))
+    if best is None or cost < best:
+      best, k = cost, i
+  ql = _fused_dense(indices[:k], mod)
+  qr = _fused_dense(indices[k:], mod)
+  nr = qr.shape[0]
+  order = np.argsort(qr, kind="stable")
+  uniq, start, cnt = np.unique(qr[order], return_index=True, return_counts=True)
+  want = np.mod(-ql, mod) if mod else -ql
+  idx = np.searchsorted(uniq, want)
+  idx_c = np.minimum(idx, uniq.shape[0] - 1)
+  valid = (idx < uniq.shape[0]) & (uniq[idx_c] == want)
+  cnt_l = np.where(valid, cnt[idx_c], 0).astype(np.int64)
+  nnz = int(cnt_l.sum())
+  if nnz == 0:
+    return np.zeros(0, dtype=np.int64)
+  l_rep = np.repeat(np.arange(ql.shape[0], dtype=np.int64), cnt_l)
+  first = np.cumsum(cnt_l) - cnt_l
+  within = np.arange(nnz, dtype=np.int64) - np.repeat(first, cnt_l)
+  return l_rep * nr + order[np.repeat(start[idx_c], cnt_l) + within].astype(np.int64)
 
 
 def _sector_maps(indices, order, partition):
@@ -444,4 +478,5 @@ def svd(tensor, pivot_axis, max_singular_values=None, max_truncation_error=None,
   V = BlockSparseTensor(v_data, [bond_v] + right, None, be)
   assert u_data.size == BlockSparseTensor._nnz([bond_u] + left) and v_data.size == BlockSparseTensor._nnz([bond_v] + right)  # pylint: disable=protected-access
   s_disc = np.concatenate(discarded) if discarded else np.zeros(0)
-  return U, dict(values=s_vals, index=bond_u, kept=kept, ktot=ktot), V, s_disc
+  disc_q = cat([np.full(len(d), qn[q], dtype=np.int64) for q, d in enumerate(discarded)]) if discarded else np.zeros(0, dtype=np.int64)
+  return U, dict(values=s_vals, index=bond_u, kept=kept, ktot=ktot, discarded=s_disc, discarded_charges=disc_q), V, s_disc

@@ -119,12 +119,28 @@ struct TcParams {
   int64_t c_cs;                       // column stride: 1 (normal) or the original row stride (swap-AB: the
                                       // kernel computes C^T tiles and stores them transposed)
   int vec_ok;
+  int c_hint;                         // 0: default L2 policy; 1: evict_last (a chained intermediate: keep it until its consumer has read it)
 };
 
 constexpr int kBM = 128;
 constexpr int kRowBytes = 128;        // one swizzle row = BK elements
 constexpr int kThreads = 256;
 
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_global_v4_hint(void* dst, const uint4& v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;"
+               ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
+}
 
 // Store one 32-column chunk of an accumulator row held by this lane (row = TMEM lane).  Normal mode: the
 // lane's 32 values are contiguous in C (vector stores).  swap-AB (c_cs != 1): the lane's row is an ORIGINAL
@@ -257,7 +273,8 @@ __device__ __forceinline__ void epilogue_drain(const TcParams& p, uint32_t taddr
         const int64_t grow = row0 + r, gcol = col0 + (int64_t)part * (16 / es);
         if (grow < p.M && gcol < p.N) {
           char* dst = (char*)p.C + (bi * p.c_sb + grow * p.c_sm + gcol) * es;
-          *(uint4*)dst = v;
+          if (p.c_hint) st_global_v4_hint(dst, v, l2_policy_evict_last());
+          else *(uint4*)dst = v;
         }
       }
       __syncwarp();
@@ -284,6 +301,13 @@ __device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap*
   asm volatile(
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm_hint(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4,
+                                                     uint64_t policy) {
+  const uint32_t leader_bar = bar & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -783,6 +807,7 @@ static int tc_prepare(const GemmProblem& g, bool chain_mode, TcPrep& o) {
   p.out_kind = g.dtype == TNB200_BF16 ? 0 : (g.dtype == TNB200_F16 ? 1 : 2);
   p.C = g.C; p.c_sm = g.c_sm; p.c_sb = g.c_sb; p.c_cs = g.swapped ? g.c_sn : 1;
   if (g.swapped && p.c_cs == 1) p.c_cs = 2;   // degenerate (M == 1): force the transposed-store path; stride unused
+  p.c_hint = 0;
   p.vec_ok = !g.swapped && (((uintptr_t)g.C) % 16 == 0) && ((g.c_sm * es) % 16 == 0) && ((g.c_sb * es) % 16 == 0);
     bool a_mn = false, b_mn = false;
   int rc = encode_operand(&o.tmA, g.dtype, g.A, g.M, g.K, g.batch, kBM, a_mn, p.a_fe, p.a_ke);
@@ -884,6 +909,7 @@ struct alignas(64) ChainStepDev {
   uint32_t need_a, need_b;        // counter value of that step's (sample) entry when it is complete
   int tiles_per_sample;
   uint32_t tx_bytes;              // bytes landing on the leader's full barrier per k-block (both CTAs)
+  int hint_a, hint_b;             // L2 policy of the operand loads: 0 default, 1 evict_first (streamed external operand), 2 evict_last (intermediate)
 };
 struct ChainSeg { long long tile0; int step, sample0, nsamples, pad; };
 struct ChainParams {
@@ -990,6 +1016,8 @@ gemm_tcgen05_chain_kernel(const __grid_constant__ ChainParams cp) {
       const int f_in = fe ? (int)((uint32_t)f % fe) : f, f_out = fe ? (int)((uint32_t)f / fe) : 0;
       const int num_kb = sd->p.num_kb;
       const uint32_t tx = sd->tx_bytes;
+      const int hint = is_a ? sd->hint_a : sd->hint_b;
+      const uint64_t policy = hint == 2 ? l2_policy_evict_last() : l2_policy_evict_first();
       // operands produced by earlier steps of this launch: wait until every tile of (that step, this sample) is out
       if (lane == 0) {
         if (sd->dep_a >= 0) chain_wait(cp.done + (size_t)sd->dep_a * cp.batch + t.bi, sd->need_a);
@@ -1008,8 +1036,13 @@ gemm_tcgen05_chain_kernel(const __grid_constant__ ChainParams cp) {
         __syncwarp();
         if (mine) {
           const uint32_t dst = smem_u32(smem + (size_t)s * STAGE_BYTES) + dst_off;
-          if (!mn) tma_load_5d_2sm(dst, map, full, k_in, f_in, f_out, k_out, t.bi);
-          else     tma_load_5d_2sm(dst, map, full, f_in, k_in, k_out, f_out, t.bi);
+          if (hint) {
+            if (!mn) tma_load_5d_2sm_hint(dst, map, full, k_in, f_in, f_out, k_out, t.bi, policy);
+            else     tma_load_5d_2sm_hint(dst, map, full, f_in, k_in, k_out, f_out, t.bi, policy);
+          } else {
+            if (!mn) tma_load_5d_2sm(dst, map, full, k_in, f_in, f_out, k_out, t.bi);
+            else     tma_load_5d_2sm(dst, map, full, f_in, k_in, k_out, f_out, t.bi);
+          }
         }
         k_in += BK;
         if (ke && (uint32_t)k_in >= ke) { k_in = 0; ++k_out; }
@@ -1143,6 +1176,23 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
     sd.need_a = sd.need_b = 0;
     if (prep.stage_bytes > max_stage) max_stage = prep.stage_bytes;
     flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)batch;
+  }
+  // L2 residency policy (TNB200_CHAIN_L2=0 turns it off): results consumed by a later step of the run are stored and
+  // re-loaded evict_last, operands that only stream through (site tensors) are loaded evict_first — so the run's
+  // intermediates live and die in L2 instead of being written back to HBM behind the streamed inputs.
+  {
+    const char* e = getenv("TNB200_CHAIN_L2");
+    const bool on = !(e && e[0] == '0');
+    std::vector<char> consumed(nsteps, 0);
+    for (int i = 0; i < nsteps; ++i) {
+      if (dep_a[i] >= 0) consumed[dep_a[i]] = 1;
+      if (dep_b[i] >= 0) consumed[dep_b[i]] = 1;
+    }
+    for (int i = 0; i < nsteps; ++i) {
+      steps[i].hint_a = on ? (dep_a[i] >= 0 ? 2 : 1) : 0;
+      steps[i].hint_b = on ? (dep_b[i] >= 0 ? 2 : 1) : 0;
+      steps[i].p.c_hint = (on && consumed[i]) ? 1 : 0;
+    }
   }
   for (int i = 0; i < nsteps; ++i) {
     if (steps[i].dep_a >= 0) steps[i].need_a = 8u * (uint32_t)steps[steps[i].dep_a].tiles_per_sample;   // 2 CTAs x 4 epilogue warps per tile

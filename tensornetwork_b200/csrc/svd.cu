@@ -428,6 +428,14 @@ __device__ __forceinline__ void pp_wait_counter(const unsigned* p, unsigned targ
   __syncthreads();
 }
 
+// pair k (0..31) of step `step` (0..62) of the round-robin tournament on 64 columns, sorted: division-free
+__device__ __forceinline__ void pp_rr(int step, int k, int& a, int& b) {
+  if (k == 0) { a = step; b = PP_PB - 1; return; }
+  int x = step + k; if (x >= PP_PB - 1) x -= PP_PB - 1;
+  int y = step - k + (PP_PB - 1); if (y >= PP_PB - 1) y -= PP_PB - 1;
+  a = x < y ? x : y; b = x < y ? y : x;
+}
+
 __global__ void __launch_bounds__(PP_THREADS, 1) svd_pair_kernel(const __grid_constant__ PairParams p) {
   extern __shared__ __align__(16) unsigned char pp_smem[];
   double* tiles = reinterpret_cast<double*>(pp_smem);                 // PP_NST x [64 cols][PP_LD]
@@ -435,7 +443,6 @@ __global__ void __launch_bounds__(PP_THREADS, 1) svd_pair_kernel(const __grid_co
   double* rm = jt + PP_PB * PP_LD;                                    // [64][65] accumulated rotation J
   double* cs = rm + PP_PB * PP_GLD;                                   // [32] cos, [32] sin
   double* sn = cs + PP_SB;
-  int* pq = reinterpret_cast<int*>(sn + PP_SB);                       // [32] p, [32] q
   __shared__ float red[8];
   __shared__ float s_off;
   double* g = jt;
@@ -560,10 +567,8 @@ __global__ void __launch_bounds__(PP_THREADS, 1) svd_pair_kernel(const __grid_co
           if (s_off <= p.tol) { if (isw == 0) rotate = false; break; }
           for (int step = 0; step < PP_PB - 1; ++step) {
             if (tid < PP_SB) {
-              const int m = PP_PB - 1;
               int a, b;
-              if (tid == 0) { a = m; b = step % m; } else { a = (step + tid) % m; b = (step - tid + m) % m; }
-              if (a > b) { int t2 = a; a = b; b = t2; }
+              pp_rr(step, tid, a, b);
               const double gpq = g[a * PP_GLD + b], app = g[a * PP_GLD + a], aqq = g[b * PP_GLD + b];
               double c = 1.0, s = 0.0;
               if (fabs(gpq) > 1e-300) {
@@ -572,26 +577,50 @@ __global__ void __launch_bounds__(PP_THREADS, 1) svd_pair_kernel(const __grid_co
                 c = rsqrt(fma(t2, t2, 1.0));
                 s = t2 * c;
               }
-              cs[tid] = c; sn[tid] = s; pq[tid] = a; pq[PP_SB + tid] = b;
+              cs[tid] = c; sn[tid] = s;
             }
             __syncthreads();
-            // G <- J^T G J: the 2 x 2 block (rows p_i,q_i x columns p_j,q_j) belongs to one thread
-            for (int blk = tid; blk < PP_SB * PP_SB; blk += PP_THREADS) {
-              const int ki = blk >> 5, kj = blk & 31;
-              const int pi = pq[ki], qi = pq[PP_SB + ki], pj = pq[kj], qj = pq[PP_SB + kj];
-              const double cj2 = cs[kj], sj2 = sn[kj], ci2 = cs[ki], si2 = sn[ki];
-              const double a = g[pi * PP_GLD + pj], b = g[pi * PP_GLD + qj], c2 = g[qi * PP_GLD + pj], d = g[qi * PP_GLD + qj];
-              const double a1 = a * cj2 - b * sj2, b1 = a * sj2 + b * cj2;
-              const double c1 = c2 * cj2 - d * sj2, d1 = c2 * sj2 + d * cj2;
-              g[pi * PP_GLD + pj] = a1 * ci2 - c1 * si2; g[qi * PP_GLD + pj] = a1 * si2 + c1 * ci2;
-              g[pi * PP_GLD + qj] = b1 * ci2 - d1 * si2; g[qi * PP_GLD + qj] = b1 * si2 + d1 * ci2;
-            }
-            for (int idx = tid; idx < PP_SB * PP_PB; idx += PP_THREADS) {
-              const int k = idx >> 6, i = idx & 63;
-              const double c = cs[k], s = sn[k];
-              const int a = pq[k], b = pq[PP_SB + k];
-              const double x = rm[i * PP_GLD + a], y = rm[i * PP_GLD + b];
-              rm[i * PP_GLD + a] = x * c - y * s; rm[i * PP_GLD + b] = x * s + y * c;
+            // G <- J^T G J: the 2 x 2 block (rows p_i,q_i x columns p_j,q_j) belongs to one thread.  Every element is in
+            // exactly one block, so all loads of a thread are issued before its first store (the compiler cannot prove that
+            // the shared-memory stores do not alias the next block's loads and would serialise the four blocks otherwise).
+            {
+              const int kj = tid & 31;
+              int pj, qj;
+              pp_rr(step, kj, pj, qj);
+              const double cj2 = cs[kj], sj2 = sn[kj];
+              int pi[4], qi[4];
+              double ci2[4], si2[4], va[4], vb[4], vc[4], vd[4];
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int ki = (tid >> 5) + it * 8;
+                pp_rr(step, ki, pi[it], qi[it]);
+                ci2[it] = cs[ki]; si2[it] = sn[ki];
+                va[it] = g[pi[it] * PP_GLD + pj]; vb[it] = g[pi[it] * PP_GLD + qj];
+                vc[it] = g[qi[it] * PP_GLD + pj]; vd[it] = g[qi[it] * PP_GLD + qj];
+              }
+              // the accumulated rotation: J[i][a], J[i][b] for 8 of the 32 rotations
+              const int ji = tid & 63;
+              int ja_[8], jb_[8];
+              double jc[8], js[8], jx[8], jy[8];
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int k = (tid >> 6) + it * 4;
+                pp_rr(step, k, ja_[it], jb_[it]);
+                jc[it] = cs[k]; js[it] = sn[k];
+                jx[it] = rm[ji * PP_GLD + ja_[it]]; jy[it] = rm[ji * PP_GLD + jb_[it]];
+              }
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const double a1 = va[it] * cj2 - vb[it] * sj2, b1 = va[it] * sj2 + vb[it] * cj2;
+                const double c1 = vc[it] * cj2 - vd[it] * sj2, d1 = vc[it] * sj2 + vd[it] * cj2;
+                g[pi[it] * PP_GLD + pj] = a1 * ci2[it] - c1 * si2[it]; g[qi[it] * PP_GLD + pj] = a1 * si2[it] + c1 * ci2[it];
+                g[pi[it] * PP_GLD + qj] = b1 * ci2[it] - d1 * si2[it]; g[qi[it] * PP_GLD + qj] = b1 * si2[it] + d1 * ci2[it];
+              }
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                rm[ji * PP_GLD + ja_[it]] = jx[it] * jc[it] - jy[it] * js[it];
+                rm[ji * PP_GLD + jb_[it]] = jx[it] * js[it] + jy[it] * jc[it];
+              }
             }
             __syncthreads();
           }

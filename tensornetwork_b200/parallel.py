@@ -155,48 +155,67 @@ def partition_tree(n_inputs, path, step_flops, world, oversub=4):
 
 
 def contract_tree_parallel(tensors, labels, out_labels, path, rank, world, contract_pair, send, recv,
-                           step_flops=None):
+                           step_flops=None, irecv=None, plan=None):
   """Execute `path` with the steps spread over `world` ranks.
 
   contract_pair(t1, labels1, t2, labels2) -> (tensor, labels)   (contract_between semantics)
-  send(tensor, dst) / recv(shape_labels_hint, src) -> tensor     (NCCL / gloo point-to-point)
-  Every rank holds all inputs.  Returns (result or None, root_rank)."""
+  send(tensor, dst)                                              (point-to-point, may be asynchronous)
+  recv(tensor_id, src) -> tensor                                 (blocking receive), or
+  irecv(tensor_id, src) -> callable returning the tensor         (receive POSTED up front, waited on at the join)
+  A subtree result consumed on another rank is sent the moment it exists (right after the step that produces it), not
+  at the join; with `irecv` every rank posts all its receives before its first contraction, per source in the order
+  the source produces them (point-to-point messages between two ranks match in order).
+  Every rank holds all inputs.  Returns (result or None, root_rank, info)."""
   n = len(tensors)
   ssa = path_to_ssa(n, path)
   if step_flops is None:
     step_flops = [1.0] * len(ssa)
-  owner, transfers, info = partition_tree(n, path, step_flops, world)
+  owner, transfers, info = plan if plan is not None else partition_tree(n, path, step_flops, world)
+  producer = {o: i for i, (_, _, o) in enumerate(ssa)}
   vals = {i: (tensors[i], list(labels[i])) for i in range(n)}
-  pending = {}
-  for t, src, dst, before in transfers:
-    pending.setdefault(before, []).append((t, src, dst))
+  outgoing = {}
+  incoming = []
+  for t, src, dst, _before in transfers:
+    if rank == src:
+      outgoing.setdefault(t, []).append(dst)
+    if rank == dst:
+      incoming.append((producer.get(t, -1), t, src))
   # labels of every intermediate are needed on the receiving side: replay them symbolically
   lab = {i: list(labels[i]) for i in range(n)}
   for a, b, o in ssa:
     shared = [l for l in lab[a] if l in lab[b]]
     lab[o] = [l for l in lab[a] if l not in shared] + [l for l in lab[b] if l not in shared]
+  handles = {}
+  incoming.sort()
+  if irecv is not None:
+    for _, t, src in incoming:
+      handles[t] = irecv(t, src)
+  arriving = {t: src for _, t, src in incoming}
   for s, (a, b, o) in enumerate(ssa):
-    for t, src, dst in pending.get(s, []):
-      if rank == src:
-        send(vals[t][0], dst)
-      elif rank == dst:
-        vals[t] = (recv(t, src), lab[t])
-    if owner[s] == rank:
-      ta, la = vals[a]
-      tb, lb = vals[b]
-      vals[o] = contract_pair(ta, la, tb, lb)
-      # free operands that are intermediates
-      for x in (a, b):
-        if x >= n:
-          vals.pop(x, None)
+    if owner[s] != rank:
+      continue
+    for x in (a, b):
+      if x not in vals and x in arriving:
+        vals[x] = ((handles.pop(x)() if x in handles else recv(x, arriving[x])), lab[x])
+    ta, la = vals[a]
+    tb, lb = vals[b]
+    vals[o] = contract_pair(ta, la, tb, lb)
+    for dst in outgoing.get(o, ()):
+      send(vals[o][0], dst)
+    # free operands that are intermediates
+    for x in (a, b):
+      if x >= n:
+        vals.pop(x, None)
   root = ssa[-1][2] if ssa else 0
   root_rank = owner[-1] if ssa else 0
   res = vals.get(root, (None, None))[0] if rank == root_rank else None
+  info = dict(info)
+  info["transfers"] = [(t, src, dst) for t, src, dst, _ in transfers]
   return res, root_rank, info
 
 
 # ------------------------------------------------------------------------ NCCL execution
-def contract_network_parallel(backend, tensors, labels, out_labels=(), path=None, step_flops=None, group=None):
+def contract_network_parallel(backend, tensors, labels, out_labels=(), path=None, step_flops=None, group=None, plan=None):
   """`contract_tree_parallel` on the CUDA backend with torch.distributed (NCCL over NVLink) as transport.
   Every rank passes the same inputs (B200Tensors or host arrays); returns (result B200Tensor on the root
   rank / None elsewhere, root_rank, info)."""
@@ -229,15 +248,183 @@ def contract_network_parallel(backend, tensors, labels, out_labels=(), path=None
     out = backend.tensordot(t1, t2, ([a1[i] for i in srt], [a2[i] for i in srt]))
     return out, [l for l in l1 if l not in shared] + [l for l in l2 if l not in shared]
 
+  keep = []                                   # isend works / buffers stay alive until the caller synchronises
+  moved = [0]
+
   def send(t, dst):
-    dist.send(backend.contiguous(t).t, dst, group=group)
+    buf = backend.contiguous(t)
+    moved[0] += buf.t.numel() * buf.t.element_size()
+    keep.append((buf, dist.isend(buf.t, dst, group=group)))
 
   def recv(tid, src):
     buf = backend._new([sizes[l] for l in lab[tid]], code)  # pylint: disable=protected-access
     dist.recv(buf.t, src, group=group)
     return buf
-  res, root_rank, info = contract_tree_parallel(ts, labels, out_labels, path, rank, world, pair, send, recv, step_flops)
+
+  def irecv(tid, src):
+    buf = backend._new([sizes[l] for l in lab[tid]], code)  # pylint: disable=protected-access
+    work = dist.irecv(buf.t, src, group=group)
+    moved[0] += buf.t.numel() * buf.t.element_size()
+
+    def ready():
+      work.wait()                             # the compute stream waits for the transfer; the host does not
+      return buf
+    return ready
+  res, root_rank, info = contract_tree_parallel(ts, labels, out_labels, path, rank, world, pair, send, recv, step_flops,
+                                                irecv=irecv, plan=plan)
+  for _, w in keep:
+    w.wait()
+  info["p2p_bytes_this_rank"] = moved[0]
   if res is not None and len(lab[ssa[-1][2]]) > 1 and list(out_labels):
     final = lab[ssa[-1][2]]
     res = backend.transpose(res, tuple(final.index(l) for l in out_labels))
   return res, root_rank, info
+
+
+# ------------------------------------------------------------------------ graph-replayed shards
+def local_subtrees(n_inputs, ssa, owner, rank):
+  """The maximal subtrees of the contraction tree that `rank` can contract without hearing from anyone: every step
+  is owned by `rank` and every operand is an input or the result of such a step.
+  Returns (roots, pure): roots = {root_tensor_id: (leaf_input_ids, steps_in_order)}, pure = set of step indices."""
+  pure, of = set(), {}
+  for s, (a, b, o) in enumerate(ssa):
+    if owner[s] != rank:
+      continue
+    if all(x < n_inputs or x in of for x in (a, b)):
+      pure.add(s)
+      of[o] = s
+  consumed = {}
+  for s, (a, b, o) in enumerate(ssa):
+    for x in (a, b):
+      consumed[x] = s
+  roots = {}
+  for o, s in of.items():
+    c = consumed.get(o)
+    if c is None or c not in pure:                       # consumed above the cut (or the network's result)
+      leaves, steps = [], []
+
+      def walk(t):
+        if t < n_inputs:
+          if t not in leaves:
+            leaves.append(t)
+          return
+        a, b, _ = ssa[of[t]]
+        walk(a)
+        walk(b)
+        steps.append(of[t])
+      walk(o)
+      roots[o] = (leaves, sorted(steps))
+  return roots, pure
+
+
+def ssa_to_linear(leaves, steps, ssa):
+  """SSA steps over the tensor ids `leaves` -> opt_einsum 'linear' path of the sub-network whose inputs are `leaves`."""
+  ids = list(leaves)
+  path = []
+  for s in steps:
+    a, b, o = ssa[s]
+    i, j = ids.index(a), ids.index(b)
+    path.append((i, j))
+    for k in sorted((i, j), reverse=True):
+      del ids[k]
+    ids.append(o)
+  return path
+
+
+class ShardedNetwork:
+  """ONE network on `world` GPUs: the pairwise path (path_contractors.py:87-90 runs it as a sequential
+  loop) is a binary tree; `partition_tree` cuts it into subtrees packed onto the ranks.  Each rank holds its local
+  subtrees as `CompiledNetwork`s (one CUDA-graph replay each) and runs the few steps above the cut eagerly; a subtree
+  result consumed on another rank is sent once, point to point (NCCL isend over NVLink) the moment it exists, into a
+  receive the consumer posted before its first contraction.  No collective on the data path."""
+
+  def __init__(self, backend, shapes, dtype, labels, path, rank, world, group=None):
+    from . import drivers  # pylint: disable=import-outside-toplevel
+    from . import tensor as T  # pylint: disable=import-outside-toplevel
+    self.backend, self.rank, self.world, self.group = backend, rank, world, group
+    n = self.n = len(shapes)
+    self.ssa = ssa = path_to_ssa(n, path)
+    sizes = {l: s[ax] for s, labs in zip(shapes, labels) for ax, l in enumerate(labs)}
+    self.sizes = sizes
+    lab = self.lab = {i: list(l) for i, l in enumerate(labels)}
+    flops = []
+    for a, b, o in ssa:
+      shared = [l for l in lab[a] if l in lab[b]]
+      lab[o] = [l for l in lab[a] if l not in shared] + [l for l in lab[b] if l not in shared]
+      k = float(np.prod([sizes[l] for l in shared])) if shared else 1.0
+      flops.append(2.0 * k * float(np.prod([sizes[l] for l in lab[o]] or [1.0])))
+    self.step_flops = flops
+    self.owner, self.transfers, self.info = partition_tree(n, path, flops, world)
+    self.producer = {o: i for i, (_, _, o) in enumerate(ssa)}
+    self.roots, self.pure = local_subtrees(n, ssa, self.owner, rank)
+    self.code = T.dtype_code(dtype)
+    self.nets = {}
+    for root, (leaves, steps) in self.roots.items():
+      sub_path = ssa_to_linear(leaves, steps, ssa)
+      self.nets[root] = (leaves, drivers.CompiledNetwork(backend, [tuple(shapes[i]) for i in leaves], dtype,
+                                                         [labels[i] for i in leaves], list(lab[root]), path=sub_path))
+    self.outgoing, self.incoming = {}, []
+    for t, src, dst, _ in self.transfers:
+      if rank == src:
+        self.outgoing.setdefault(t, []).append(dst)
+      if rank == dst:
+        self.incoming.append((self.producer.get(t, -1), t, src))
+    self.incoming.sort()
+    self.inputs = None
+    self.p2p_bytes = 0
+
+  def load(self, tensors):
+    """static inputs (every rank holds all of them; only the ones its steps touch are copied into graph arenas)"""
+    self.inputs = list(tensors)
+    for root, (leaves, net) in self.nets.items():
+      net.load([tensors[i] for i in leaves])
+
+  def _pair(self, t1, l1, t2, l2):
+    shared = [l for l in l1 if l in l2]
+    a1 = [l1.index(l) for l in shared]
+    a2 = [l2.index(l) for l in shared]
+    srt = sorted(range(len(a1)), key=lambda i: a1[i])
+    return self.backend.tensordot(t1, t2, ([a1[i] for i in srt], [a2[i] for i in srt]))
+
+  def run(self):
+    """-> (result B200Tensor on the root rank / None elsewhere, root_rank).  Stream-ordered; nothing blocks the host
+    except NCCL's own enqueue."""
+    import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+    be, rank, lab = self.backend, self.rank, self.lab
+    handles, keep = {}, []
+    moved = 0
+    for _, t, src in self.incoming:
+      buf = be._new([self.sizes[l] for l in lab[t]], self.code)  # pylint: disable=protected-access
+      handles[t] = (buf, dist.irecv(buf.t, src, group=self.group))
+      moved += buf.t.numel() * buf.t.element_size()
+    vals = {}
+
+    def emit(o, tensor):
+      nonlocal moved
+      vals[o] = tensor
+      for dst in self.outgoing.get(o, ()):
+        buf = be.contiguous(tensor)
+        moved += buf.t.numel() * buf.t.element_size()
+        keep.append((buf, dist.isend(buf.t, dst, group=self.group)))
+    for root, (_, net) in self.nets.items():
+      emit(root, net())
+
+    def get(x):
+      if x < self.n:
+        return self.inputs[x]
+      if x not in vals and x in handles:
+        buf, work = handles.pop(x)
+        work.wait()                      # the compute stream waits for the transfer; the host does not
+        vals[x] = buf
+      return vals[x]
+    for s, (a, b, o) in enumerate(self.ssa):
+      if self.owner[s] != rank or s in self.pure:
+        continue
+      emit(o, self._pair(get(a), lab[a], get(b), lab[b]))
+    for _, w in keep:
+      w.wait()
+    self._keep = keep
+    self.p2p_bytes = moved
+    root_rank = self.owner[-1] if self.ssa else 0
+    res = vals.get(self.ssa[-1][2]) if (self.ssa and rank == root_rank) else None
+    return res, root_rank

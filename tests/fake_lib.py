@@ -233,3 +233,58 @@ class FakeLib:
     _view(q)[...] = Q
     _view(r)[...] = R
     return 0
+
+  # ---- block-sparse entry points (host memory): raw pointers + element counts
+  @staticmethod
+  def _vec(ptr, n, dt):
+    dt = np.dtype(dt)
+    if n == 0:
+      return np.zeros(0, dtype=dt)
+    return np.ndarray((n,), dtype=dt, buffer=(ctypes.c_char * (n * dt.itemsize)).from_address(int(ptr)))
+
+  def tnb200_gather(self, src, idx, dst, n, dtype, scatter, stream):
+    n = int(n)
+    if n == 0:
+      return 0
+    ix = self._vec(idx, n, np.int64)
+    hi = int(ix.max()) + 1
+    if scatter:
+      self._vec(dst, hi, _NP[dtype])[ix] = self._vec(src, n, _NP[dtype])
+    else:
+      self._vec(dst, n, _NP[dtype])[...] = self._vec(src, hi, _NP[dtype])[ix]
+    self._launches += 1
+    return 0
+
+  def tnb200_blocksparse_tensordot(self, a, b, c, dtype, nsect, dims, am, ao, bm, bo, cm, co, max_m, max_n, conj_b, stream):
+    nsect = int(nsect)
+    d = self._vec(dims, 3 * nsect, np.int64).reshape(nsect, 3)
+    aoff, boff, coff = (self._vec(p, nsect + 1, np.int64) for p in (ao, bo, co))
+    amap, bmap, cmap = self._vec(am, int(aoff[-1]), np.int64), self._vec(bm, int(boff[-1]), np.int64), self._vec(cm, int(coff[-1]), np.int64)
+    A = self._vec(a, int(amap.max()) + 1, _NP[dtype])
+    B = self._vec(b, int(bmap.max()) + 1, _NP[dtype])
+    C = self._vec(c, int(cmap.max()) + 1, _NP[dtype])
+    for q in range(nsect):
+      m, k, n = (int(x) for x in d[q])
+      x = A[amap[aoff[q]:aoff[q + 1]]].reshape(m, k)
+      y = B[bmap[boff[q]:boff[q + 1]]].reshape(k, n)
+      C[cmap[coff[q]:coff[q + 1]]] = (x @ (np.conj(y) if conj_b else y)).ravel()
+    self._launches += 1
+    return 0
+
+  def tnb200_svd_batched(self, a, dtype, nprob, dims, aoff, u, uoff, s, soff, vh, voff, max_m, max_n, status, stream):
+    nprob = int(nprob)
+    d = self._vec(dims, 2 * nprob, np.int64).reshape(nprob, 2)
+    ao, uo, so, vo = (self._vec(p, nprob + 1, np.int64) for p in (aoff, uoff, soff, voff))
+    rdt = np.zeros(0, dtype=_NP[dtype]).real.dtype
+    A, U = self._vec(a, int(ao[-1]), _NP[dtype]), self._vec(u, int(uo[-1]), _NP[dtype])
+    S, V = self._vec(s, int(so[-1]), rdt), self._vec(vh, int(vo[-1]), _NP[dtype])
+    for q in range(nprob):
+      m, n = int(d[q, 0]), int(d[q, 1])
+      uu, ss, vv = np.linalg.svd(A[ao[q]:ao[q + 1]].reshape(m, n), full_matrices=False)
+      U[uo[q]:uo[q + 1]] = uu.ravel()
+      S[so[q]:so[q + 1]] = ss
+      V[vo[q]:vo[q + 1]] = vv.ravel()
+    if status:
+      self._vec(status, 1, np.int32)[0] = 0
+    self._launches += 1
+    return 0

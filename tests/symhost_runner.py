@@ -1,0 +1,25 @@
+"""Runs in a subprocess: the symmetric_b200 adapter (tensornetwork_b200/symmetric.py) driven by the REAL reference's callers
+(block-sparse tn.Node @, split_node, ncon, backend.svd) with the device layer replaced by tests/fake_lib.FakeLib (host memory):
+checks the conversion between the reference's BlockSparseTensor and the elementary-leg form the kernels take."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from baseline import refenv
+tn = refenv.load()
+from tensornetwork_b200 import _lib, backend as tb_backend
+import fake_lib
+_lib.set_lib(fake_lib.FakeLib())
+tb_backend._CONFIG["device"] = "cpu"
+import tensornetwork_b200 as tb
+assert tb.registered_symmetric
+import importlib.util, types
+spec = importlib.util.spec_from_file_location("tsym", os.path.join(ROOT, "tests", "test_gpu_symmetric_adapter.py"))
+m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+m.test_registered_and_tensordot_matches_reference(tn); print("tensordot ok")
+m.test_nodes_and_split_node_on_blocksparse_tensors(tn); print("nodes/split ok")
+for kw in [{}, {"max_singular_values": 7}, {"max_truncation_error": 0.2}, {"max_truncation_error": 0.1, "relative": True}]:
+    m.test_svd_matches_reference(tn, kw)
+print("svd ok")
+m.test_ncon_two_site_matvec_on_blocksparse_tensors(tn); print("ncon ok")
+print("SYMHOST OK")

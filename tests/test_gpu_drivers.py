@@ -262,4 +262,9 @@ def test_cfg2_full_size_fp64_vs_oracle_and_scaling_property():
   # and within bf16 tolerance of the fp64 oracle on the same (bf16-rounded) inputs, sample 0
   ts = [d.to_host()[0].astype(np.float64) for d in dev]
   exact = nn.contract_path(ts + [np.conj(t) for t in ts], labels, path, [])
-  assert abs(base[0] - exact) <= 0.15 * abs(exact)      # 127 bf16-rounded steps, ket/bra errors coherent
+  # 127 steps with bf16-rounded intermediates (2^-9 relative each, ket and bra halves coherent): stated tolerance 3e-2,
+  # checked on every sample of the batch (measured ~1e-2)
+  for b in range(NB):
+    tb_ = [d.to_host()[b].astype(np.float64) for d in dev]
+    ex = nn.contract_path(tb_ + [np.conj(t) for t in tb_], labels, path, [])
+    assert abs(base[b] - ex) <= 3e-2 * abs(ex), (b, base[b], ex)

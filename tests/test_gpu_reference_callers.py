@@ -144,3 +144,39 @@ def test_cfg5_two_site_update_full_bond_dimension(tn, D):
   assert np.linalg.norm(th_g - th_n) <= 1e-7 * np.linalg.norm(th_n) or np.linalg.norm(th_g + th_n) <= 1e-7 * np.linalg.norm(th_n)
   ug = u_g.reshape(-1, D)
   np.testing.assert_allclose(ug.T @ ug, np.eye(D), atol=1e-9)
+
+
+def test_reference_ncon_reaches_graph_replay_through_jit(tn):
+  """`tn.ncon` -> `backend.jit(_jittable_ncon, static_argnums=(1..5))` (ncon_interface.py:654-660): call 1 eager, call 2
+  captures the reference's own python loop in a CUDA graph, call 3 is ONE graph launch (no kernel launched from the host)
+  on NEW input data, result equal to the numpy backend's."""
+  be = _backend(tn)
+  rng = np.random.default_rng(8)
+  net = [[-1, 1, 2], [1, 3, -2], [2, 3, 4], [4, -3]]
+
+  def data():
+    return [rng.standard_normal(s) for s in ((6, 7, 8), (7, 9, 5), (8, 9, 4), (4, 3))]
+  stats0 = dict(be.jit_stats)
+  for call in range(4):
+    xs = data()
+    n0 = be.lib.tnb200_launch_count()
+    r0 = be.jit_stats["replays"]
+    got = tn.ncon([be.convert_to_tensor(x) for x in xs], net, backend="cuda_b200")
+    launched = be.lib.tnb200_launch_count() - n0
+    ref = tn.ncon(xs, net, backend="numpy")
+    np.testing.assert_allclose(np.asarray(got), ref, rtol=0, atol=1e-12 * np.abs(ref).max())
+    if call >= 2:
+      assert launched == 0, (call, launched)                     # nothing but the graph replay
+      assert be.jit_stats["replays"] - r0 == 1
+  assert be.jit_stats["captures"] - stats0["captures"] == 1
+  # results are values, not views of the captured buffers: an earlier result survives later calls
+  keep = tn.ncon([be.convert_to_tensor(x) for x in xs], net, backend="cuda_b200")
+  keep_host = np.asarray(keep).copy()
+  tn.ncon([be.convert_to_tensor(x) for x in data()], net, backend="cuda_b200")
+  np.testing.assert_array_equal(np.asarray(keep), keep_host)
+  # a function that synchronises with the host (truncating svd) falls back to eager, permanently, without error
+  f = be.jit(lambda t: be.svd(t, 1, max_truncation_error=1e-3, relative=True)[1], static_argnums=())
+  x = be.convert_to_tensor(rng.standard_normal((20, 12)))
+  a = [np.asarray(f(x)) for _ in range(3)]
+  np.testing.assert_allclose(a[0], a[2])
+  np.testing.assert_allclose(a[0], tn.backends.backend_factory.get_backend("numpy").svd(np.asarray(x), 1, max_truncation_error=1e-3, relative=True)[1], atol=1e-12)

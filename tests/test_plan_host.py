@@ -84,3 +84,48 @@ def test_find_chains_on_cfg2():
   assert all(len(r) >= 2 for r in runs)
   flat = [i for r in runs for i in r]
   assert len(flat) == len(set(flat))
+
+
+def test_local_subtrees_cover_the_partition_exactly():
+  """parallel.local_subtrees / ssa_to_linear (the graph-replayed shards of ShardedNetwork): on every rank the local
+  subtrees plus the steps above the cut are exactly the steps the rank owns, and replaying each subtree's linear
+  sub-path with numpy reproduces the intermediate the full path produces."""
+  import sys, os
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+  from tensornetwork_b200 import parallel
+  from oracle import np_network as nn
+  rng = np.random.default_rng(5)
+  n_nodes, chi, d = 10, 4, 2
+  parent = [-1] + [int(rng.integers(0, i)) for i in range(1, n_nodes)]
+  lk = [["p%d" % i] for i in range(n_nodes)]
+  lb = [["p%d" % i] for i in range(n_nodes)]
+  sizes = {"p%d" % i: d for i in range(n_nodes)}
+  for i in range(1, n_nodes):
+    for tag, L in (("k", lk), ("b", lb)):
+      e = "%s%d_%d" % (tag, parent[i], i)
+      L[i].append(e); L[parent[i]].append(e); sizes[e] = chi
+  labels = lk + lb
+  tensors = [rng.standard_normal([sizes[l] for l in labs]) for labs in labels]
+  path = nn.greedy_path(labels, [], sizes)
+  n = len(labels)
+  ssa = parallel.path_to_ssa(n, path)
+  flops = [2.0 * m * k * nn_ for m, k, nn_ in nn.network_flops(labels, path, sizes)]
+  # full replay: value and labels of every intermediate
+  vals = {i: (tensors[i], list(labels[i])) for i in range(n)}
+  for a, b, o in ssa:
+    vals[o] = nn.contract_between(vals[a][0], vals[a][1], vals[b][0], vals[b][1])
+  for world in (2, 3, 4):
+    owner, transfers, info = parallel.partition_tree(n, path, flops, world)
+    seen = set()
+    for rank in range(world):
+      roots, pure = parallel.local_subtrees(n, ssa, owner, rank)
+      assert all(owner[s] == rank for s in pure)
+      covered = set()
+      for root, (leaves, steps) in roots.items():
+        covered |= set(steps)
+        sub = parallel.ssa_to_linear(leaves, steps, ssa)
+        got = nn.contract_path([tensors[i] for i in leaves], [labels[i] for i in leaves], sub, vals[root][1])
+        np.testing.assert_allclose(got, vals[root][0], rtol=1e-12, atol=1e-12)
+      assert covered == pure
+      seen |= {s for s in range(len(ssa)) if owner[s] == rank}
+    assert seen == set(range(len(ssa)))

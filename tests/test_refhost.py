@@ -27,3 +27,11 @@ def test_reference_callers_on_cuda_b200_adapter():
 def test_reference_two_site_dmrg_on_cuda_b200_adapter():
   out = _run("--dmrg")
   assert "case dmrg ok" in out
+
+
+def test_reference_blocksparse_callers_on_symmetric_b200_adapter():
+  """tests/symhost_runner.py: block-sparse tn.Node @ / split_node / ncon / svd on backend="symmetric_b200" against the
+  reference's backend="symmetric" (host double of the library)."""
+  r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "symhost_runner.py")],
+                     capture_output=True, text=True, cwd=ROOT, timeout=600)
+  assert r.returncode == 0 and "SYMHOST OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
