@@ -187,6 +187,20 @@ TNB200_API int32_t tnb200_svd_batched(const void* a_data, int32_t dtype, int32_t
                                       const int64_t* s_off_dev, void* vh_data, const int64_t* vh_off_dev,
                                       int64_t max_m, int64_t max_n, int32_t* status_dev, void* stream);
 
+/* ---- f3: the int64 element maps of a block-sparse matrix view, built on the device (the reference builds them on the host
+ * with numpy unique / intersect: block_sparse/blocksparse_utils.py:330-634, cached only on request, caching.py:22-88).
+ * The tensor has `nlegs` stored legs; leg t has dims[t] states with SIGNED charges (flow applied, int64) at
+ * charges_dev[leg_off[t] ...].  Matrix view: rows = legs order[0..partition), columns = order[partition..nlegs).
+ * Output map_dev[nnz]: sector-major (ascending row charge), inside a sector row-major (rows x columns, both ascending):
+ * the position in the data vector of every element — bit-identical to the reference's maps.  `split` cuts the stored legs
+ * into the two groups whose states are enumerated; shift = sum of max|charge| over the legs (U(1)), modulus = N for Z_N
+ * (0: U(1)); nbins = 2*shift+1 or N; tables_dev = int64 [start_right(nbins) | sect_off(nbins) | ncols(nbins)], the
+ * per-charge tables the caller derives from the legs' charge histograms (charge-degeneracy arithmetic).
+ * dims / leg_off / order are HOST arrays. */
+TNB200_API int32_t tnb200_blocksparse_maps(int32_t nlegs, const int64_t* dims, const int64_t* charges_dev, const int64_t* leg_off,
+                                           const int32_t* order, int32_t partition, int32_t split, int64_t modulus, int64_t shift,
+                                           int32_t nbins, const int64_t* tables_dev, int64_t nnz, int64_t* map_dev, void* stream);
+
 /* dst[i] = src[idx[i]] (gather) or dst[idx[i]] = src[i] (scatter = 1), i < n; idx is a device int64 array.
  * The fancy-index gathers of block_sparse (blocksparsetensor.py:1094-1101, symmetric decompositions.py:55). */
 TNB200_API int32_t tnb200_gather(const void* src, const int64_t* idx_dev, void* dst, int64_t n, int32_t dtype,

@@ -78,6 +78,9 @@ class CudaB200Backend(_Base):
     self.math_mode = L.MATH_DEFAULT
     self._seed = 0x5EED
     self._jit_cache = {}
+    self._capturing = 0             # > 0 while jit.JitFunction records a CUDA graph
+    self._cap_stream = None
+    T._SYNC_GUARD[0] = self._no_capture
     self.jit_graphs = os.environ.get("TNB200_JIT", "1") != "0"      # jit(): CUDA-graph capture (0 = identity, like numpy's)
     self.jit_stats = {"eager": 0, "captures": 0, "replays": 0, "capture_failures": 0}
     if _INSTANCE is None:
@@ -88,6 +91,18 @@ class CudaB200Backend(_Base):
     if self._on_cuda:
       return self.torch.cuda.current_stream().cuda_stream
     return 0
+
+  def _capture_stream(self):
+    if self._cap_stream is None:
+      self._cap_stream = self.torch.cuda.Stream()
+    return self._cap_stream
+
+  def _no_capture(self, what):
+    """Host-synchronising operations cannot be part of a CUDA graph: refuse cleanly (before any CUDA call) so that
+    jit.JitFunction falls back to eager execution for this function."""
+    if self._capturing:
+      from .jit import CaptureUnsupported  # pylint: disable=import-outside-toplevel
+      raise CaptureUnsupported(what + " synchronises with the host and cannot be captured in a CUDA graph")
 
   def _new(self, shape, code):
     return B200Tensor(self.torch.empty(tuple(int(s) for s in shape), dtype=T.code_to_torch(code),
@@ -283,6 +298,7 @@ class CudaB200Backend(_Base):
     code = T.dtype_code(arr.dtype)  # raises TypeError for unsupported dtypes
     if not arr.flags.c_contiguous or not arr.flags.writeable:
       arr = np.array(arr, order="C")
+    self._no_capture("convert_to_tensor(host array)")
     return B200Tensor(torch.from_numpy(arr).to(self.device, non_blocking=False), code)
 
   def from_host(self, array, dtype=None):
@@ -577,6 +593,7 @@ class CudaB200Backend(_Base):
           relative=False):
     """backends/numpy/decompositions.py:21-74 -> (u, s, vh, s_rest)."""
     self._check_type(tensor)
+    self._no_capture("svd")          # (cooperative persistent launch / data-dependent kept count)
     mat, left, right = self._as_matrix(tensor, pivot_axis)
     if mat.code in (L.I32, L.I64, L.F16, L.BF16):
       raise TypeError("svd needs a float32/float64/complex tensor")

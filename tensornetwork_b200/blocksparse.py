@@ -16,6 +16,7 @@ per (charges, flows, order, partition) signature on the host (pure integer work,
 checked bit-exactly against the reference's maps in tests/) and ALL sectors run in ONE launch
 of the grouped kernel `tnb200_blocksparse_tensordot`.
 """
+import os
 import numpy as np
 from . import _lib as L
 from . import tensor as T
@@ -135,6 +136,107 @@ def _sector_maps(indices, order, partition):
   return out
 
 
+def _group_hist(indices, legs, shift, mod, nbins):
+  """Number of states of the product space of `legs` per fused signed charge, in the global charge bins
+  (U(1): bin = q + shift; Z_N: bin = q mod N): charge-degeneracy arithmetic — a convolution of the legs' charge
+  histograms; the product space itself is never enumerated."""
+  if mod:
+    h = np.zeros(mod, dtype=np.int64)
+    h[0] = 1
+    for t in legs:
+      ht = np.bincount(np.mod(_signed(indices[t]), mod), minlength=mod).astype(np.int64)
+      full = np.convolve(h, ht)
+      h = np.zeros(mod, dtype=np.int64)
+      np.add.at(h, np.arange(full.shape[0]) % mod, full)
+    return h
+  h = np.ones(1, dtype=np.int64)
+  lo = 0                                     # charge of h[0]
+  for t in legs:
+    q = _signed(indices[t])
+    qmin = int(q.min()) if q.size else 0
+    ht = np.bincount(q - qmin).astype(np.int64) if q.size else np.zeros(1, dtype=np.int64)
+    h = np.convolve(h, ht)
+    lo += qmin
+  out = np.zeros(nbins, dtype=np.int64)
+  out[lo + shift:lo + shift + h.shape[0]] = h
+  return out
+
+
+def _count_allowed(indices):
+  """number of stored elements (total signed charge zero) from the legs' charge histograms alone"""
+  if not indices:
+    return 1
+  mod = indices[0].modulus
+  shift = 0 if mod else int(sum(int(np.abs(_signed(ix)).max()) if ix.dim else 0 for ix in indices))
+  nbins = int(mod) if mod else 2 * shift + 1
+  h = _group_hist(indices, list(range(len(indices))), shift, mod, nbins)
+  return int(h[0] if mod else h[shift])
+
+
+def _device_sector_maps(be, indices, order, partition):
+  """`_sector_maps` with the element map built ON THE DEVICE (tnb200_blocksparse_maps).
+
+  Returns (qnums, dims (nsect x 2), dev_map (1-D int64 device tensor, all sectors, ascending charge), offs (nsect + 1)).
+  The host computes only the per-charge tables (a few dozen integers: histogram convolutions of the legs)."""
+  key = ("dsect", tuple(ix.key() for ix in indices), tuple(order), partition)
+  hit = _MAP_CACHE.get(key)
+  if hit is not None:
+    return hit
+  import ctypes  # pylint: disable=import-outside-toplevel
+  torch = be.torch
+  n = len(indices)
+  if n == 0:                                  # a scalar: one 1 x 1 sector holding data[0]
+    out = (np.zeros(1, dtype=np.int64), np.ones((1, 2), dtype=np.int64), torch.zeros(1, dtype=torch.int64, device=be.device),
+           np.array([0, 1], dtype=np.int64))
+    _MAP_CACHE[key] = out
+    return out
+  mod = indices[0].modulus if indices else None
+  dims = [ix.dim for ix in indices]
+  signed = [_signed(ix).astype(np.int64) for ix in indices]
+  shift = 0 if mod else int(sum(int(np.abs(q).max()) if q.size else 0 for q in signed))
+  nbins = int(mod) if mod else 2 * shift + 1
+  partner = (lambda b: (mod - b) % mod) if mod else (lambda b: 2 * shift - b)
+  # split of the STORED legs into two balanced groups (as _fused_allowed does)
+  total, best, split, left = int(np.prod(dims)) if dims else 1, None, 1, 1
+  for i in range(1, n + 1):
+    left *= dims[i - 1]
+    cost = max(left, total // max(left, 1))
+    if best is None or cost < best:
+      best, split = cost, i
+  stored = list(range(n))
+  rows, cols = list(order[:partition]), list(order[partition:])
+  h_left = _group_hist(indices, stored[:split], shift, mod, nbins)
+  h_right = _group_hist(indices, stored[split:], shift, mod, nbins)
+  h_row = _group_hist(indices, rows, shift, mod, nbins)
+  h_col = _group_hist(indices, cols, shift, mod, nbins)
+  pb = np.array([partner(b) for b in range(nbins)], dtype=np.int64)
+  nnz = int((h_left * h_right[pb]).sum())
+  start_right = np.zeros(nbins, dtype=np.int64)
+  start_right[1:] = np.cumsum(h_right)[:-1]
+  ncols = h_col[pb]
+  sizes = h_row * ncols
+  sect_off = np.zeros(nbins, dtype=np.int64)
+  sect_off[1:] = np.cumsum(sizes)[:-1]
+  live = np.nonzero(sizes > 0)[0]
+  qnums = live.astype(np.int64) if mod else (live - shift).astype(np.int64)
+  sdims = np.stack([h_row[live], ncols[live]], axis=1).astype(np.int64).reshape(-1, 2)
+  offs = np.append(sect_off[live], nnz).astype(np.int64)
+  assert int(sizes.sum()) == nnz
+  leg_off = np.zeros(n, dtype=np.int64)
+  leg_off[1:] = np.cumsum(dims)[:-1]
+  charges_dev = torch.from_numpy(np.concatenate(signed) if signed else np.zeros(1, dtype=np.int64)).to(be.device)
+  tables_dev = torch.from_numpy(np.concatenate([start_right, sect_off, ncols])).to(be.device)
+  dev_map = torch.empty(max(nnz, 1), dtype=torch.int64, device=be.device)
+  i64 = lambda xs: (ctypes.c_int64 * max(len(xs), 1))(*[int(x) for x in xs])
+  i32 = lambda xs: (ctypes.c_int32 * max(len(xs), 1))(*[int(x) for x in xs])
+  L.check(be.lib.tnb200_blocksparse_maps(n, i64(dims), charges_dev.data_ptr(), i64(leg_off), i32(order), int(partition), int(split),
+                                          int(mod or 0), int(shift), nbins, tables_dev.data_ptr(), nnz, dev_map.data_ptr(),
+                                          be._stream()))  # pylint: disable=protected-access
+  out = (qnums, sdims, dev_map, offs)
+  _MAP_CACHE[key] = out
+  return out
+
+
 class BlockSparseTensor:
   """Block-sparse tensor whose `data` vector lives in HBM (a 1-D B200Tensor)."""
 
@@ -151,7 +253,7 @@ class BlockSparseTensor:
     key = ("nnz", tuple(ix.key() for ix in indices))
     hit = _MAP_CACHE.get(key)
     if hit is None:
-      hit = int(_fused_allowed(indices).shape[0])
+      hit = _count_allowed(indices)
       _MAP_CACHE[key] = hit
     return hit
 
@@ -303,9 +405,15 @@ def tensordot(a, b, axes):
   # matrix views: A = (free_a | axes_a), B = (axes_b | free_b), C = (free_a | free_b)
   order_a = [a.order[i] for i in free_a] + [a.order[i] for i in axes_a]
   order_b = [b.order[i] for i in axes_b] + [b.order[i] for i in free_b]
-  qa, da, ma = _sector_maps(a.indices, order_a, len(free_a))
-  qb, db, mb = _sector_maps(b.indices, order_b, len(axes_b))
-  qc, dc, mc = _sector_maps(out_indices, list(range(len(out_indices))), len(free_a))
+  host_maps = os.environ.get("TNB200_BS_HOST_MAPS", "0") == "1"       # measurement / debugging knob: numpy-built maps
+  if host_maps:
+    qa, da, ma = _sector_maps(a.indices, order_a, len(free_a))
+    qb, db, mb = _sector_maps(b.indices, order_b, len(axes_b))
+    qc, dc, mc = _sector_maps(out_indices, list(range(len(out_indices))), len(free_a))
+  else:
+    qa, da, ma, oa = _device_sector_maps(be, a.indices, order_a, len(free_a))
+    qb, db, mb, ob = _device_sector_maps(be, b.indices, order_b, len(axes_b))
+    qc, dc, mc, oc = _device_sector_maps(be, out_indices, list(range(len(out_indices))), len(free_a))
   nnz_c = BlockSparseTensor._nnz(out_indices)  # pylint: disable=protected-access
   c_data = be.zeros((nnz_c,), a.data.dtype)      # blocksparsetensor.py:1088: zero-initialised
   mod = a.indices[0].modulus if a.indices else None
@@ -329,18 +437,23 @@ def tensordot(a, b, axes):
   dev = _MAP_CACHE.get(key)
   if dev is None:
     torch = be.torch
-    dims = np.asarray([[s[3], s[4], s[5]] for s in sect], dtype=np.int64)
-
-    def cat(maps, which):
-      arrs = [maps[s[which]] for s in sect]
-      off = np.zeros(len(arrs) + 1, dtype=np.int64)
-      off[1:] = np.cumsum([x.shape[0] for x in arrs])
-      return np.concatenate(arrs), off
-    am, ao = cat(ma, 0)
-    bm, bo = cat(mb, 1)
-    cm, co = cat(mc, 2)
+    dims = np.array([[m_, k_, n_] for (_, _, _, m_, k_, n_) in sect], dtype=np.int64)
     up = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(be.device)
-    dev = dict(dims=up(dims), am=up(am), ao=up(ao), bm=up(bm), bo=up(bo), cm=up(cm), co=up(co),
+    if host_maps:
+      def cat(maps, which):
+        arrs = [maps[sc[which]] for sc in sect]
+        off = np.zeros(len(arrs) + 1, dtype=np.int64)
+        off[1:] = np.cumsum([x.shape[0] for x in arrs])
+        return up(np.concatenate(arrs)), off
+      am, ao = cat(ma, 0)
+      bm, bo = cat(mb, 1)
+      cm, co = cat(mc, 2)
+    else:
+      # the device maps hold every sector of their tensor; a contraction sector starts at that sector's offset
+      am, ao = ma, np.array([oa[sc[0]] for sc in sect] + [0], dtype=np.int64)
+      bm, bo = mb, np.array([ob[sc[1]] for sc in sect] + [0], dtype=np.int64)
+      cm, co = mc, np.array([oc[sc[2]] for sc in sect] + [0], dtype=np.int64)
+    dev = dict(dims=up(dims), am=am, ao=up(ao), bm=bm, bo=up(bo), cm=cm, co=up(co),
                max_m=int(dims[:, 0].max()), max_n=int(dims[:, 2].max()), nsect=len(sect),
                keep=(ma, mb, mc), flops=float(2 * (dims[:, 0] * dims[:, 1] * dims[:, 2]).sum()))
     _MAP_CACHE[key] = dev

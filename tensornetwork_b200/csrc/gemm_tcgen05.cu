@@ -309,6 +309,19 @@ __device__ __forceinline__ void tma_load_5d_2sm_hint(uint32_t dst, const CUtenso
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
       ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(policy) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d_2sm_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4,
+                                                   uint16_t cta_mask) {
+  // multicast to every CTA of `cta_mask` (same CTA-relative destination); with cta_group::2 the transaction bytes are
+  // signalled on the barrier of each destination's PAIR LEADER (peer bit cleared)
+  const uint32_t leader_bar = bar & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "h"(cta_mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm_mask(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -904,6 +917,7 @@ int gemm_chain_destroy(void* handle);
 // ever waits for tiles that are earlier in the sequence: no deadlock.
 struct alignas(64) ChainStepDev {
   CUtensorMap tmA, tmB;
+  CUtensorMap tmAh;               // A with a 64-row box (K-major operands): one half of a CTA's slab, for the 4-CTA multicast kernel
   TcParams p;
   int dep_a, dep_b;               // chain step that produces operand a / b (-1: available before the launch)
   uint32_t need_a, need_b;        // counter value of that step's (sample) entry when it is complete
@@ -1134,6 +1148,201 @@ gemm_tcgen05_chain_kernel(const __grid_constant__ ChainParams cp) {
   }
 }
 
+// ---- 4-CTA clusters: two cta_group::2 pairs side by side in N share their A slabs by TMA multicast.
+// The 2-CTA chain kernel is bound by the L2 -> SM operand feed (128 flop per L2 byte: 16 KB of A + 16 KB of B per CTA and
+// k-block).  Here a cluster holds pair 0 = ranks {0, 1} on tile (mi, 2j) and pair 1 = ranks {2, 3} on tile (mi, 2j + 1):
+// both pairs need the same 256 x BK block of A.  Rank r loads only HALF of its 128-row slab (half = r >> 1) and multicasts
+// it to the CTA of the other pair that stages the same slab (mask {r & 1, (r & 1) + 2}); every CTA still receives its
+// whole slab, but issues 8 KB + 16 KB instead of 16 KB + 16 KB per k-block: 171 flop per L2 byte.
+//   * full barriers: unchanged accounting — each pair leader expects 2 x stage bytes; multicast bytes are signalled on the
+//     leader of every destination CTA (cta_group::2, peer bit cleared);
+//   * empty barriers: a stage is written by BOTH pairs' producers, so it is released by BOTH pairs' MMA commits
+//     (count 2, tcgen05.commit multicast to all four CTAs): the two pairs advance k-block by k-block together;
+//   * accumulator barriers stay pair-local (commit mask 0b0011 / 0b1100).
+// Tiles are dealt to clusters two at a time (2 st, 2 st + 1): needs an even number of N tiles in every step.
+template <int KIND>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tcgen05_chain4_kernel(const __grid_constant__ ChainParams cp) {
+  constexpr int ES = KIND == 0 ? 2 : 4;
+  constexpr int BK = kRowBytes / ES;
+  constexpr int CHUNK = kRowBytes / ES;
+  constexpr int A_BYTES = kBM * kRowBytes;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int STAGE_BYTES = cp.stage_bytes;
+  const int S = cp.stages;
+  uint64_t* bars = (uint64_t*)(smem + (size_t)S * STAGE_BYTES);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S + 2 + a); };
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+  const uint32_t epi_slab = (smem_u32(tmem_slot) + 16 + 15) & ~15u;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0..3
+  const uint32_t pr = rank & 1;                     // rank inside the cta_group::2 pair
+  const uint32_t pair_in = rank >> 1;               // which pair of the cluster = which half of the A slab this CTA loads
+  const uint32_t pair_leader = rank & ~1u;
+  const bool leader = pr == 0;
+  const uint16_t pair_mask = (uint16_t)(3u << pair_leader);
+  const uint16_t a_mask = (uint16_t)((1u << pr) | (1u << (pr + 2)));
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 2); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long first = 2 * (long long)(blockIdx.x >> 2) + pair_in, step = 2 * (long long)(gridDim.x >> 2);
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (all four CTAs, whole warp)
+    int s = 0; uint32_t ph = 0;
+    int cursor = 0;
+    for (long long tile = first; tile < cp.num_tiles; tile += step) {
+      ChainTile t;
+      const ChainStepDev* sd = chain_decode(cp, tile, cursor, t);
+      const int BN = sd->p.BN, b_rows = BN / 2;
+      const int a_mn = sd->p.a_mn, b_mn = sd->p.b_mn;
+      const int nA = a_mn ? (kBM / CHUNK) / 2 : 1;            // boxes of MY half of the slab
+      const int nB = b_mn ? b_rows / CHUNK : 1;
+      const bool mine = lane < nA + nB;
+      const bool is_a = lane < nA;
+      const bool mn = is_a ? (a_mn != 0) : (b_mn != 0);
+      const uint32_t fe = is_a ? sd->p.a_fe : sd->p.b_fe, ke = is_a ? sd->p.a_ke : sd->p.b_ke;
+      const CUtensorMap* map = is_a ? (a_mn ? &sd->tmA : &sd->tmAh) : &sd->tmB;
+      int f;
+      uint32_t dst_off;
+      if (is_a) {
+        if (mn) { const int c = (int)pair_in * nA + lane; f = t.mi * 2 * kBM + (int)pr * kBM + c * CHUNK; dst_off = (uint32_t)c * (BK * kRowBytes); }
+        else { f = t.mi * 2 * kBM + (int)pr * kBM + (int)pair_in * (kBM / 2); dst_off = pair_in * (uint32_t)(A_BYTES / 2); }
+      } else {
+        const int c = lane - nA;
+        f = t.ni * BN + (int)pr * b_rows + (mn ? c * CHUNK : 0);
+        dst_off = (uint32_t)A_BYTES + (mn ? (uint32_t)c * (BK * kRowBytes) : 0u);
+      }
+      const int f_in = fe ? (int)((uint32_t)f % fe) : f, f_out = fe ? (int)((uint32_t)f / fe) : 0;
+      const int num_kb = sd->p.num_kb;
+      const uint32_t tx = sd->tx_bytes;
+      if (lane == 0) {
+        if (sd->dep_a >= 0) chain_wait(cp.done + (size_t)sd->dep_a * cp.batch + t.bi, sd->need_a);
+        if (sd->dep_b >= 0) chain_wait(cp.done + (size_t)sd->dep_b * cp.batch + t.bi, sd->need_b);
+      }
+      __syncwarp();
+      asm volatile("fence.proxy.async;" ::: "memory");
+      int k_in = 0, k_out = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(s), ph ^ 1);                      // both pairs have consumed this stage (here AND in the twin CTA)
+        const uint32_t full = full_bar(s);
+        if (lane == 0) {
+          if (leader) mbar_expect_tx(full, tx);
+          else mbar_arrive_remote(full, pair_leader);
+        }
+        __syncwarp();
+        if (mine) {
+          const uint32_t dst = smem_u32(smem + (size_t)s * STAGE_BYTES) + dst_off;
+          if (is_a) {
+            if (!mn) tma_load_5d_2sm_mc(dst, map, full, k_in, f_in, f_out, k_out, t.bi, a_mask);
+            else     tma_load_5d_2sm_mc(dst, map, full, f_in, k_in, k_out, f_out, t.bi, a_mask);
+          } else {
+            if (!mn) tma_load_5d_2sm(dst, map, full, k_in, f_in, f_out, k_out, t.bi);
+            else     tma_load_5d_2sm(dst, map, full, f_in, k_in, k_out, f_out, t.bi);
+          }
+        }
+        k_in += BK;
+        if (ke && (uint32_t)k_in >= ke) { k_in = 0; ++k_out; }
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ===================================================== MMA issuer (the leader of each pair)
+    int s = 0; uint32_t ph = 0;
+    int acc = 0; uint32_t acc_ph = 0;
+    int cursor = 0;
+    for (long long tile = first; tile < cp.num_tiles; tile += step) {
+      ChainTile t;
+      const ChainStepDev* sd = chain_decode(cp, tile, cursor, t);
+      const int a_mn = sd->p.a_mn, b_mn = sd->p.b_mn, num_kb = sd->p.num_kb;
+      const uint32_t idesc = sd->p.idesc;
+      const uint32_t a_layout = (a_mn && KIND == 1) ? 1u : 2u;
+      const uint32_t b_layout = (b_mn && KIND == 1) ? 1u : 2u;
+      const uint32_t a_lbo = a_mn ? BK * kRowBytes : 0u, b_lbo = b_mn ? BK * kRowBytes : 0u;
+      const uint32_t a_sbo = (a_mn && KIND == 1) ? 512u : 1024u;
+      const uint32_t b_sbo = (b_mn && KIND == 1) ? 512u : 1024u;
+      const uint32_t a_kstep = a_mn ? (32u / ES) * kRowBytes : 32u;
+      const uint32_t b_kstep = b_mn ? (32u / ES) * kRowBytes : 32u;
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, a_layout);
+          const uint64_t bd = make_smem_desc(sb + k * b_kstep, b_lbo, b_sbo, b_layout);
+          if (!cp.debug_no_mma) tc_mma_2sm<KIND>(d_tmem, ad, bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        tc_commit_2sm_mask(empty_bar(s), (uint16_t)0xF);      // this pair is done with stage s in all four CTAs' view
+        if (kb == num_kb - 1) tc_commit_2sm_mask(tfull_bar(acc), pair_mask);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue (all CTAs: their own 128 rows)
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_ph = 0;
+    int cursor = 0;
+    uint32_t* pending = nullptr;
+    auto publish = [&]() {
+      if (pending != nullptr) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) red_release_add_u32(pending, 1u);
+        pending = nullptr;
+      }
+    };
+    for (long long tile = first; tile < cp.num_tiles; tile += step) {
+      ChainTile t;
+      const ChainStepDev* sd = chain_decode(cp, tile, cursor, t);
+      const TcParams p = sd->p;
+      const int64_t row = (int64_t)t.mi * 2 * kBM + (int64_t)pr * kBM + q * 32 + lane;
+      const int64_t n0 = (int64_t)t.ni * p.BN;
+      if (!mbar_test(tfull_bar(acc), acc_ph)) publish();
+      mbar_wait(tfull_bar(acc), acc_ph);
+      publish();
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256);
+      epilogue_drain(p, taddr0, p.BN, t.bi, row - lane, lane, n0, epi_slab + (uint32_t)q * kSlabBytes);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (leader) mbar_arrive(tempty_bar(acc)); else mbar_arrive_remote(tempty_bar(acc), pair_leader); }
+      pending = cp.done + (size_t)t.step * cp.batch + t.bi;
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+    publish();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------- chain: host side
 struct ChainHandle {
   ChainStepDev* d_steps = nullptr;
@@ -1141,6 +1350,7 @@ struct ChainHandle {
   uint32_t* d_done = nullptr;
   ChainParams cp;
   int kind = 0, nsteps = 0;
+  int cl = 2;                     // CTAs per cluster: 2 (one pair) or 4 (two pairs sharing A by multicast)
   size_t smem = 0, done_bytes = 0;
   unsigned grid = 0;
   double flops = 0.0;
@@ -1159,6 +1369,8 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
   std::vector<ChainStepDev> steps(nsteps);
   int max_stage = 0;
   double flops = 0.0;
+  bool cl4_ok = true;
+  { const char* e = getenv("TNB200_CHAIN_CL"); if (!(e && e[0] == '4')) cl4_ok = false; }   // opt-in until validated: TNB200_CHAIN_CL=4
   for (int i = 0; i < nsteps; ++i) {
     const GemmProblem& g = probs[i];
     if (g.dtype != dtype || g.batch != batch || g.conjA || g.conjB) return TNB200_ERR_UNSUPPORTED;
@@ -1170,6 +1382,13 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
     if (rc) return rc;
     ChainStepDev& sd = steps[i];
     sd.tmA = prep.tmA; sd.tmB = prep.tmB; sd.p = prep.p;
+    sd.tmAh = prep.tmA;
+    if (!prep.p.a_mn) {           // K-major A: a second map whose box is half a slab (64 rows) for the multicast kernel
+      bool mn2 = false; uint32_t fe2 = 0, ke2 = 0;
+      if (encode_operand(&sd.tmAh, g.dtype, g.A, g.M, g.K, g.batch, kBM / 2, mn2, fe2, ke2) != 0 || mn2 || fe2 != prep.p.a_fe || ke2 != prep.p.a_ke)
+        cl4_ok = false;
+    }
+    if (prep.p.tiles_n % 2) cl4_ok = false;
     sd.dep_a = dep_a[i]; sd.dep_b = dep_b[i];
     sd.tiles_per_sample = (int)(prep.p.tiles_m * prep.p.tiles_n);
     sd.tx_bytes = (uint32_t)(2 * prep.stage_bytes);
@@ -1177,21 +1396,23 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
     if (prep.stage_bytes > max_stage) max_stage = prep.stage_bytes;
     flops += 2.0 * (double)g.M * (double)g.N * (double)g.K * (double)batch;
   }
-  // L2 residency policy (TNB200_CHAIN_L2=0 turns it off): results consumed by a later step of the run are stored and
-  // re-loaded evict_last, operands that only stream through (site tensors) are loaded evict_first — so the run's
-  // intermediates live and die in L2 instead of being written back to HBM behind the streamed inputs.
+  // L2 residency policy, TNB200_CHAIN_L2 = bit mask (measurement knob; default 0 = hardware default policy):
+  //   1: operands produced by an earlier step of the run are loaded evict_last
+  //   2: operands that only stream through (site tensors) are loaded evict_first
+  //   4: results consumed by a later step are stored evict_last
+  // Measured on cfg 2 (bf16, 74 networks): all three together cost 7 % (3.76 ms vs 3.52 ms per launch) — see DESIGN.md.
   {
     const char* e = getenv("TNB200_CHAIN_L2");
-    const bool on = !(e && e[0] == '0');
+    const int mask = e ? atoi(e) : 0;
     std::vector<char> consumed(nsteps, 0);
     for (int i = 0; i < nsteps; ++i) {
       if (dep_a[i] >= 0) consumed[dep_a[i]] = 1;
       if (dep_b[i] >= 0) consumed[dep_b[i]] = 1;
     }
     for (int i = 0; i < nsteps; ++i) {
-      steps[i].hint_a = on ? (dep_a[i] >= 0 ? 2 : 1) : 0;
-      steps[i].hint_b = on ? (dep_b[i] >= 0 ? 2 : 1) : 0;
-      steps[i].p.c_hint = (on && consumed[i]) ? 1 : 0;
+      steps[i].hint_a = dep_a[i] >= 0 ? ((mask & 1) ? 2 : 0) : ((mask & 2) ? 1 : 0);
+      steps[i].hint_b = dep_b[i] >= 0 ? ((mask & 1) ? 2 : 0) : ((mask & 2) ? 1 : 0);
+      steps[i].p.c_hint = ((mask & 4) && consumed[i]) ? 1 : 0;
     }
   }
   for (int i = 0; i < nsteps; ++i) {
@@ -1254,12 +1475,19 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
   h->smem = (size_t)stages * max_stage + (2 * stages + 4) * 8 + 32 + 4 * kSlabBytes + 1024;
   const long long np = tile0 < pairs ? tile0 : pairs;
   h->grid = (unsigned)(2 * np);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[h->kind]) {
-    e = h->kind == 0 ? cudaFuncSetAttribute(gemm_tcgen05_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-                     : cudaFuncSetAttribute(gemm_tcgen05_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  // two pairs per cluster sharing A by multicast when every step has an even number of N tiles and the grid is full
+  h->cl = (cl4_ok && np == pairs && (pairs % 2) == 0 && (tile0 % 2) == 0) ? 4 : 2;
+  static bool attr_set[4] = {false, false, false, false};
+  const int ai = h->kind + (h->cl == 4 ? 2 : 0);
+  if (!attr_set[ai]) {
+    if (h->cl == 4)
+      e = h->kind == 0 ? cudaFuncSetAttribute(gemm_tcgen05_chain4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                       : cudaFuncSetAttribute(gemm_tcgen05_chain4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    else
+      e = h->kind == 0 ? cudaFuncSetAttribute(gemm_tcgen05_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                       : cudaFuncSetAttribute(gemm_tcgen05_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) { set_error("chain: cannot raise dynamic smem: %s", cudaGetErrorString(e)); gemm_chain_destroy(h); return TNB200_ERR_CUDA; }
-    attr_set[h->kind] = true;
+    attr_set[ai] = true;
   }
   *handle = h;
   return 0;
@@ -1269,11 +1497,16 @@ int gemm_chain_launch(void* handle, cudaStream_t st) {
   ChainHandle* h = (ChainHandle*)handle;
   if (!h) return TNB200_ERR_INVALID;
   TNB_CHECK_CUDA(cudaMemsetAsync(h->d_done, 0, h->done_bytes, st));
-  if (h->kind == 0) gemm_tcgen05_chain_kernel<0><<<h->grid, kThreads, h->smem, st>>>(h->cp);
-  else gemm_tcgen05_chain_kernel<1><<<h->grid, kThreads, h->smem, st>>>(h->cp);
+  if (h->cl == 4) {
+    if (h->kind == 0) gemm_tcgen05_chain4_kernel<0><<<h->grid, kThreads, h->smem, st>>>(h->cp);
+    else gemm_tcgen05_chain4_kernel<1><<<h->grid, kThreads, h->smem, st>>>(h->cp);
+  } else {
+    if (h->kind == 0) gemm_tcgen05_chain_kernel<0><<<h->grid, kThreads, h->smem, st>>>(h->cp);
+    else gemm_tcgen05_chain_kernel<1><<<h->grid, kThreads, h->smem, st>>>(h->cp);
+  }
   TNB_LAUNCH_CHECK();
   count_launch();
-  set_kernel_name(h->kind == 0 ? "tcgen05_chain_16" : "tcgen05_chain_tf32");
+  set_kernel_name(h->kind == 0 ? (h->cl == 4 ? "tcgen05_chain4_16" : "tcgen05_chain_16") : (h->cl == 4 ? "tcgen05_chain4_tf32" : "tcgen05_chain_tf32"));
   return 0;
 }
 

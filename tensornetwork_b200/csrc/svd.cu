@@ -398,7 +398,7 @@ struct PairParams {
   unsigned* conv;                        // [max_sweeps] float bits of the largest relative off-diagonal seen in a sweep
   unsigned* bar;                         // grid barrier counter
   int32_t* info;                         // [0] sweeps, [1] converged
-  int nb, npairs, C, teams, max_sweeps, inner_sweeps;
+  int nb, npairs, C, teams, max_sweeps, inner_sweeps, full_every;
   float tol;
 };
 
@@ -429,7 +429,10 @@ __device__ __forceinline__ void pp_wait_counter(const unsigned* p, unsigned targ
 }
 
 // pair k (0..31) of step `step` (0..62) of the round-robin tournament on 64 columns, sorted: division-free
-__device__ __forceinline__ void pp_rr(int step, int k, int& a, int& b) {
+// `cross` schedule: only the 32 x 32 pairs between the two blocks of the pair (column k of block i with column
+// (k + step) mod 32 of block j, 32 steps) — the pairs INSIDE a block were rotated when the block was last visited by a full schedule
+__device__ __forceinline__ void pp_rr(int step, int k, int& a, int& b, bool cross = false) {
+  if (cross) { a = k; b = PP_SB + ((k + step) & (PP_SB - 1)); return; }
   if (k == 0) { a = step; b = PP_PB - 1; return; }
   int x = step + k; if (x >= PP_PB - 1) x -= PP_PB - 1;
   int y = step - k + (PP_PB - 1); if (y >= PP_PB - 1) y -= PP_PB - 1;
@@ -565,10 +568,13 @@ __global__ void __launch_bounds__(PP_THREADS, 1) svd_pair_kernel(const __grid_co
           }
           __syncthreads();
           if (s_off <= p.tol) { if (isw == 0) rotate = false; break; }
-          for (int step = 0; step < PP_PB - 1; ++step) {
+          // full cyclic schedule (63 steps) every p.full_every-th round, cross-block schedule (32 steps) otherwise
+          const bool cross = p.full_every > 1 && (r % p.full_every) != 0;
+          const int nsteps = cross ? PP_SB : PP_PB - 1;
+          for (int step = 0; step < nsteps; ++step) {
             if (tid < PP_SB) {
               int a, b;
-              pp_rr(step, tid, a, b);
+              pp_rr(step, tid, a, b, cross);
               const double gpq = g[a * PP_GLD + b], app = g[a * PP_GLD + a], aqq = g[b * PP_GLD + b];
               double c = 1.0, s = 0.0;
               if (fabs(gpq) > 1e-300) {
@@ -586,14 +592,14 @@ __global__ void __launch_bounds__(PP_THREADS, 1) svd_pair_kernel(const __grid_co
             {
               const int kj = tid & 31;
               int pj, qj;
-              pp_rr(step, kj, pj, qj);
+              pp_rr(step, kj, pj, qj, cross);
               const double cj2 = cs[kj], sj2 = sn[kj];
               int pi[4], qi[4];
               double ci2[4], si2[4], va[4], vb[4], vc[4], vd[4];
 #pragma unroll
               for (int it = 0; it < 4; ++it) {
                 const int ki = (tid >> 5) + it * 8;
-                pp_rr(step, ki, pi[it], qi[it]);
+                pp_rr(step, ki, pi[it], qi[it], cross);
                 ci2[it] = cs[ki]; si2[it] = sn[ki];
                 va[it] = g[pi[it] * PP_GLD + pj]; vb[it] = g[pi[it] * PP_GLD + qj];
                 vc[it] = g[qi[it] * PP_GLD + pj]; vd[it] = g[qi[it] * PP_GLD + qj];
@@ -605,7 +611,7 @@ __global__ void __launch_bounds__(PP_THREADS, 1) svd_pair_kernel(const __grid_co
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
                 const int k = (tid >> 6) + it * 4;
-                pp_rr(step, k, ja_[it], jb_[it]);
+                pp_rr(step, k, ja_[it], jb_[it], cross);
                 jc[it] = cs[k]; js[it] = sn[k];
                 jx[it] = rm[ji * PP_GLD + ja_[it]]; jy[it] = rm[ji * PP_GLD + jb_[it]];
               }
@@ -692,7 +698,10 @@ __global__ void __launch_bounds__(PP_THREADS, 1) svd_pair_kernel(const __grid_co
     }
     __syncthreads();
     sweeps_done = sweep + 1;
-    if (s_off <= p.tol) { converged = 1; break; }
+    // converged when no pair exceeded the tolerance — or when the largest relative off-diagonal seen (BEFORE its rotation)
+    // was below 1e-8: Jacobi converges quadratically, the rotations of this sweep left off-diagonals of order 1e-16 and a
+    // further, Gram-only sweep would only confirm it
+    if (s_off <= p.tol || s_off <= 1e-8f) { converged = 1; break; }
     __syncthreads();
   }
   if (blockIdx.x == 0 && tid == 0 && p.info) { p.info[0] = sweeps_done; p.info[1] = converged; }
@@ -746,6 +755,11 @@ static int svd_pair_real(const tnb200_tensor_t* a, const tnb200_tensor_t* u, con
   const char* e_sw = getenv("TNB200_SVD_INNER_SWEEPS");
   p.inner_sweeps = e_sw ? atoi(e_sw) : 1;
   if (p.inner_sweeps < 1) p.inner_sweeps = 1;
+  // rotation schedule inside a pair: the full 64-column cyclic sweep every 4th round, only the 32 x 32 cross-block pairs in
+  // between (numpy model of this kernel, n = 1024: 15 sweeps either way; cross-only in ALL but the first round: 16)
+  const char* e_fe = getenv("TNB200_SVD_FULL_EVERY");
+  p.full_every = e_fe ? atoi(e_fe) : 4;
+  if (p.full_every < 1) p.full_every = 1;
   p.tol = (float)(4.0 * sqrt((double)R) * 2.220446049250313e-16);
   const size_t smem = sizeof(double) * ((size_t)PP_NST * PP_PB * PP_LD + PP_PB * PP_LD + PP_PB * PP_GLD + 2 * PP_SB) + sizeof(int) * 2 * PP_SB + 16;
   static bool attr_done = false;

