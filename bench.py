@@ -920,6 +920,7 @@ def run_config(args):
   """One JSON line per configuration, same keys as the headline line where they apply (N = 1)."""
   import torch
   torch.cuda.set_device(0)
+  _ref_tn()                       # the reference first: tensornetwork_b200 then subclasses its AbstractBackend and registers in its factory
   import tensornetwork_b200 as tb
   from tensornetwork_b200 import drivers
   from oracle import np_backend as nb, np_network as nn          # cpu_baseline leg only
@@ -999,7 +1000,10 @@ def run_config(args):
     nbt = 64
     A = be.astype(be.randn((nbt, 1024, 512), np.float32, seed=2) * (1.0 / np.sqrt(512)), be_dt)
     B = be.astype(be.randn((nbt, 512, 1024), np.float32, seed=3) * (1.0 / np.sqrt(512)), be_dt)
-    ms = _time_gpu(lambda: be.matmul(A, B), steps, args.warmup)
+    def ten():                      # 10 launches per timed region: the ~10 us of host launch path per call is not kernel time
+      for _ in range(10):
+        be.matmul(A, B)
+    ms = _time_gpu(ten, steps, args.warmup) / 10.0
     kern = lib.tnb200_last_kernel().decode()
     flops, byts = nbt * 2.0 * 1024 * 512 * 1024, nbt * (1024 * 512 * 2 + 1024 * 1024) * esize
     out = be.matmul(A, B)

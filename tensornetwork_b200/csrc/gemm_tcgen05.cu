@@ -1350,6 +1350,7 @@ struct ChainHandle {
   uint32_t* d_done = nullptr;
   ChainParams cp;
   int kind = 0, nsteps = 0;
+  int clusters = 0;
   int cl = 2;                     // CTAs per cluster: 2 (one pair) or 4 (two pairs sharing A by multicast)
   size_t smem = 0, done_bytes = 0;
   unsigned grid = 0;
@@ -1477,6 +1478,28 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
   h->grid = (unsigned)(2 * np);
   // two pairs per cluster sharing A by multicast when every step has an even number of N tiles and the grid is full
   h->cl = (cl4_ok && np == pairs && (pairs % 2) == 0 && (tile0 % 2) == 0) ? 4 : 2;
+  if (h->cl == 4) {
+    // every cluster must be resident (tiles wait on each other): a cluster lives inside one GPC, so fewer than SMs / 4
+    // clusters may fit — ask the runtime, and keep the 2-CTA kernel when too many SMs would stay idle
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = h->smem; cfg.stream = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    cudaError_t qe = h->kind == 0 ? cudaFuncSetAttribute(gemm_tcgen05_chain4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                                  : cudaFuncSetAttribute(gemm_tcgen05_chain4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (qe == cudaSuccess)
+      qe = h->kind == 0 ? cudaOccupancyMaxActiveClusters(&ncl, gemm_tcgen05_chain4_kernel<0>, &cfg)
+                        : cudaOccupancyMaxActiveClusters(&ncl, gemm_tcgen05_chain4_kernel<1>, &cfg);
+    if (qe != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+    if (ncl > pairs / 2) ncl = (int)(pairs / 2);
+    const int min_cl = env_int("TNB200_CHAIN_CL4_MIN", (int)(pairs / 2) * 3 / 4);
+    if (ncl >= min_cl && ncl >= 1) h->grid = (unsigned)(4 * ncl);
+    else h->cl = 2;
+    h->clusters = ncl;
+    if (env_int("TNB200_CHAIN_VERBOSE", 0)) fprintf(stderr, "[tnb200] chain: 4-CTA clusters resident %d of %d -> cl = %d, grid = %u\n", ncl, (int)(pairs / 2), h->cl, h->grid);
+  }
   static bool attr_set[4] = {false, false, false, false};
   const int ai = h->kind + (h->cl == 4 ? 2 : 0);
   if (!attr_set[ai]) {

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "cplx.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace tnb {
 
@@ -96,6 +97,319 @@ __global__ void qr_writeout_kernel(const T* __restrict__ W, const T* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Blocked Householder QR for real matrices (compact WY, LAPACK geqrf / orgqr structure): panels of 32 columns.
+//   qr_panel_kernel : ONE cluster of 8 CTAs factors a panel.  The panel lives in shared memory, its rows dealt to the CTAs;
+//                     per column ONE cluster-wide all-reduce through distributed shared memory carries everything the
+//                     reflector needs (sigma^2 = x^T x and the products x^T a_c with all later panel columns come from the
+//                     same pass; the pivot-row entries a_jc ride in the same message), then v, tau and the rank-1 update of
+//                     the rest of the panel are local.  Ends with T of the compact-WY form (larft) from V^T V.
+//   qr_apply_kernel : X[j0:, cols] <- (I - V T' V^T) X for a block of 32 columns per CTA: W1 = V^T X (DMMA), W2 = T' W1,
+//                     X -= V W2 (DMMA) — the trailing update (T' = T^T) and, on the identity, the formation of Q (T' = T).
+// 3 launches per 32 columns instead of 3 per column; reflector convention unchanged (beta = -sign(alpha) |x|), so the
+// factors still agree element-wise with numpy's.
+constexpr int QB = 32, QCL = 8, QLD = 68;
+
+__device__ __forceinline__ void qr_dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint32_t qr_cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void qr_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store a double into the shared memory of CTA `rank` of the cluster at the address corresponding to local pointer p
+__device__ __forceinline__ void qr_st_remote(double* p, uint32_t rank, double v) {
+  uint32_t a = (uint32_t)__cvta_generic_to_shared(p), r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(r), "d"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(QCL, 1, 1) __launch_bounds__(256, 1)
+qr_panel_kernel(double* __restrict__ W, int64_t m, int j0, int b, int rl, double* __restrict__ tau, double* __restrict__ Tout,
+                double* __restrict__ Z) {
+  extern __shared__ __align__(16) double qsm[];
+  const int RLP = rl + (rl & 1);
+  double* P = qsm;                               // [QB][RLP]: this CTA's rows of the panel, column-major
+  double* part = P + (size_t)QB * RLP;           // [2][QCL][64]
+  double* mine = part + 2 * QCL * 64;            // [64]
+  double* tot = mine + 64;                       // [64]
+  double* taus = tot + 64;                       // [QB]
+  double* Ts = taus + QB;                        // [QB][QB + 1]  (rank 0 only)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = qr_cluster_rank();
+  const int64_t row0 = (int64_t)j0 + (int64_t)rank * rl;          // first global row of this CTA
+  int64_t nl64 = m - row0; if (nl64 > rl) nl64 = rl; if (nl64 < 0) nl64 = 0;
+  const int nl = (int)nl64;                                       // local rows
+  for (int idx = tid; idx < b * nl; idx += 256) {
+    const int c = idx / nl, i = idx - c * nl;
+    P[c * RLP + i] = W[(int64_t)(j0 + c) * m + row0 + i];
+  }
+  if (tid < QB) taus[tid] = 0.0;
+  __syncthreads();
+  const int nsteps = (int64_t)b < m - j0 ? b : (int)(m - j0);
+  for (int j = 0; j < nsteps; ++j) {
+    const int64_t gp = (int64_t)j0 + j;                           // global pivot row
+    int is = (int)(gp + 1 - row0); if (is < 0) is = 0;            // first local row strictly below the pivot
+    const bool own = gp >= row0 && gp < row0 + nl;
+    const int jl = (int)(gp - row0);
+    if (tid < 64) mine[tid] = 0.0;
+    __syncthreads();
+    // partial products of column j (rows below the pivot) with columns j .. b-1: one warp per column, strided
+    const double* xj = P + j * RLP;
+    for (int c = j + warp; c < b; c += 8) {
+      const double* ac = P + c * RLP;
+      double acc = 0.0;
+      for (int i = is + lane; i < nl; i += 32) acc = fma(xj[i], ac[i], acc);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+      if (lane == 0) mine[c] = acc;
+    }
+    if (own && tid >= j && tid < b) mine[32 + tid] = P[tid * RLP + jl];      // pivot-row entries a_jc (c = j: alpha)
+    __syncthreads();
+    const int buf = j & 1;
+    if (tid < 64) {
+      const double v = mine[tid];
+#pragma unroll
+      for (uint32_t q = 0; q < QCL; ++q) qr_st_remote(part + ((size_t)buf * QCL + rank) * 64 + tid, q, v);
+    }
+    qr_cluster_sync();
+    if (tid < 64) {
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < QCL; ++q) t += part[((size_t)buf * QCL + q) * 64 + tid];
+      tot[tid] = t;
+    }
+    __syncthreads();
+    const double sigma2 = tot[j], alpha = tot[32 + j];
+    if (sigma2 != 0.0) {
+      const double nrm = sqrt(alpha * alpha + sigma2);
+      const double beta = alpha >= 0.0 ? -nrm : nrm;
+      const double scale = 1.0 / (alpha - beta);
+      const double tj = (beta - alpha) / beta;
+      // rank-1 update of the later panel columns with the UNSCALED x (v_i = x_i * scale), then scale column j
+      const int nrows = nl - is;
+      if (nrows > 0) {
+        for (int idx = tid; idx < (b - j - 1) * nrows; idx += 256) {
+          const int c = j + 1 + idx / nrows, i = is + idx % nrows;
+          const double wc = tj * (tot[32 + c] + tot[c] * scale);
+          P[c * RLP + i] -= wc * (xj[i] * scale);
+        }
+      }
+      if (own) {
+        for (int c = j + 1 + tid; c < b; c += 256) P[c * RLP + jl] -= tj * (tot[32 + c] + tot[c] * scale);
+      }
+      __syncthreads();
+      for (int i = is + tid; i < nl; i += 256) P[j * RLP + i] *= scale;
+      if (own && tid == 0) P[j * RLP + jl] = beta;
+      if (tid == 0) taus[j] = tj;
+    }
+    __syncthreads();
+  }
+  // write the factored panel back (R above / on the diagonal, V below)
+  for (int idx = tid; idx < b * nl; idx += 256) {
+    const int c = idx / nl, i = idx - c * nl;
+    W[(int64_t)(j0 + c) * m + row0 + i] = P[c * RLP + i];
+  }
+  // Z = V^T V (strict upper part) for larft: v(i,k) = 0 above the diagonal of the panel, 1 on it, P below
+  for (int idx = tid; idx < b * b; idx += 256) {
+    const int k = idx / b, jj = idx % b;
+    if (k >= jj) continue;
+    double acc = 0.0;
+    int i0 = (int)((int64_t)j0 + jj - row0); if (i0 < 0) i0 = 0;            // rows >= pivot of the LATER column jj
+    for (int i = i0; i < nl; ++i) {
+      const int64_t gi = row0 + i;
+      const double vk = P[k * RLP + i];                                     // gi >= j0 + jj > j0 + k: below k's pivot
+      const double vj = gi == (int64_t)j0 + jj ? 1.0 : P[jj * RLP + i];
+      acc = fma(vk, vj, acc);
+    }
+    if (acc != 0.0) atomicAdd(&Z[k * QB + jj], acc);
+  }
+  __threadfence();
+  qr_cluster_sync();
+  if (rank == 0) {
+    if (tid < b) tau[tid] = taus[tid];
+    for (int idx = tid; idx < QB * (QB + 1); idx += 256) Ts[idx] = 0.0;
+    __syncthreads();
+    for (int jj = 0; jj < b; ++jj) {                                        // T(0:jj, jj) = -tau_jj T(0:jj, 0:jj) Z(0:jj, jj)
+      if (tid < jj) {
+        double acc = 0.0;
+        for (int l = tid; l < jj; ++l) acc = fma(Ts[tid * (QB + 1) + l], __ldcg(&Z[l * QB + jj]), acc);
+        Ts[tid * (QB + 1) + jj] = -taus[jj] * acc;
+      }
+      if (tid == jj) Ts[jj * (QB + 1) + jj] = taus[jj];
+      __syncthreads();
+    }
+    for (int idx = tid; idx < QB * QB; idx += 256) Tout[idx] = Ts[(idx / QB) * (QB + 1) + idx % QB];
+  }
+}
+
+// X[j0:, c0 + 32 blockIdx.x ...] <- (I - V T' V^T) X ; V = unit lower trapezoid stored in W[j0:, j0:j0+b], T' = transT ? T^T : T
+__global__ void __launch_bounds__(256) qr_apply_kernel(const double* __restrict__ W, int64_t m, int j0, int b, const double* __restrict__ T,
+                                                       int transT, double* __restrict__ X, int64_t ldx, int c0, int ncols) {
+  extern __shared__ __align__(16) double qasm[];
+  double (*tv)[QB * QLD] = reinterpret_cast<double (*)[QB * QLD]>(qasm);                      // V tile  [2][k][row]
+  double (*tx)[QB * QLD] = reinterpret_cast<double (*)[QB * QLD]>(qasm + 2 * QB * QLD);       // X tile  [2][c][row]
+  double* w1 = qasm + 4 * QB * QLD;
+  double* w2 = w1 + QB * (QB + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fk = lane & 3;
+  const int cb = c0 + blockIdx.x * QB;
+  const int nc = ncols - blockIdx.x * QB < QB ? ncols - blockIdx.x * QB : QB;
+  const int64_t R = m - j0;
+  const int ntiles = (int)((R + 63) / 64);
+  // element (col e_c, rows e_r + 8 i) of a 32 x 64 tile for this thread: 8 elements per operand
+  const int e_c = tid >> 3, e_r = tid & 7;
+  double pv[8], px[8];
+  auto fetch = [&](int t) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = e_r + 8 * i;
+      const int64_t gi = (int64_t)j0 + (int64_t)t * 64 + r;
+      double v = 0.0, x = 0.0;
+      if (gi < m) {
+        if (e_c < b) {
+          const int64_t piv = (int64_t)j0 + e_c;
+          v = gi > piv ? W[(int64_t)(j0 + e_c) * m + gi] : (gi == piv ? 1.0 : 0.0);
+        }
+        if (e_c < nc) x = X[(int64_t)(cb + e_c) * ldx + gi];
+      }
+      pv[i] = v; px[i] = x;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tv[buf][e_c * QLD + e_r + 8 * i] = pv[i]; tx[buf][e_c * QLD + e_r + 8 * i] = px[i]; }
+  };
+  // ---- pass 1: W1[k][c] = sum_rows V[row][k] X[row][c]      (16 output tiles of 8 x 8, two per warp)
+  const int mt = warp >> 1, nt0 = (warp & 1) * 2;
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  int buf = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) fetch(t + 1);
+    const double* av = tv[buf];
+    const double* bx = tx[buf];
+#pragma unroll
+    for (int k4 = 0; k4 < 64; k4 += 4) {
+      const double a = av[(mt * 8 + fr) * QLD + k4 + fk];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) qr_dmma(acc[j][0], acc[j][1], a, bx[((nt0 + j) * 8 + fr) * QLD + k4 + fk]);
+    }
+    if (t + 1 < ntiles) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    w1[(mt * 8 + fr) * (QB + 1) + (nt0 + j) * 8 + 2 * fk] = acc[j][0];
+    w1[(mt * 8 + fr) * (QB + 1) + (nt0 + j) * 8 + 2 * fk + 1] = acc[j][1];
+  }
+  __syncthreads();
+  // ---- W2 = T' W1
+  for (int idx = tid; idx < QB * QB; idx += 256) {
+    const int k = idx >> 5, c = idx & 31;
+    double s = 0.0;
+    if (k < b) {
+      for (int l = 0; l < b; ++l) {
+        const double tkl = transT ? T[l * QB + k] : T[k * QB + l];
+        s = fma(tkl, w1[l * (QB + 1) + c], s);
+      }
+    }
+    w2[k * (QB + 1) + c] = s;
+  }
+  __syncthreads();
+  // ---- pass 2: X^T[c][row] -= sum_k W2[k][c] V^T[k][row]     (warp: 8 columns x 32 rows of every tile)
+  const int ct = warp >> 1, rh = (warp & 1) * 32;
+  double wa[8];
+#pragma unroll
+  for (int k4 = 0; k4 < 8; ++k4) wa[k4] = w2[(k4 * 4 + fk) * (QB + 1) + ct * 8 + fr];
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  buf = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    if (t + 1 < ntiles) fetch(t + 1);
+    const double* av = tv[buf];
+    double oc[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { oc[j][0] = 0.0; oc[j][1] = 0.0; }
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) qr_dmma(oc[j][0], oc[j][1], wa[k4], av[(k4 * 4 + fk) * QLD + rh + j * 8 + fr]);
+    const int c = ct * 8 + fr;
+    if (c < nc) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = rh + j * 8 + 2 * fk;
+        const int64_t gi = (int64_t)j0 + (int64_t)t * 64 + r;
+        double* dst = X + (int64_t)(cb + c) * ldx + gi;
+        if (gi < m) dst[0] = tx[buf][c * QLD + r] - oc[j][0];
+        if (gi + 1 < m) dst[1] = tx[buf][c * QLD + r + 1] - oc[j][1];
+      }
+    }
+    if (t + 1 < ntiles) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+}
+
+static int qr_blocked_f64(const tnb200_tensor_t* a, const tnb200_tensor_t* q, const tnb200_tensor_t* r, int nonneg, cudaStream_t st) {
+  const int64_t m = a->shape[0], n = a->shape[1];
+  const int k = (int)(m < n ? m : n);
+  const int npan = (k + QB - 1) / QB;
+  double *W = nullptr, *Q = nullptr, *tau = nullptr, *Tb = nullptr, *Z = nullptr;
+  int rc;
+  if ((rc = ws_alloc((void**)&W, sizeof(double) * (size_t)m * n, st))) return rc;
+  if ((rc = ws_alloc((void**)&Q, sizeof(double) * (size_t)m * k, st))) return rc;
+  if ((rc = ws_alloc((void**)&tau, sizeof(double) * (size_t)(k + QB), st))) return rc;
+  if ((rc = ws_alloc((void**)&Tb, sizeof(double) * (size_t)npan * QB * QB, st))) return rc;
+  if ((rc = ws_alloc((void**)&Z, sizeof(double) * (size_t)npan * QB * QB, st))) return rc;
+  TNB_CHECK_CUDA(cudaMemsetAsync(Z, 0, sizeof(double) * (size_t)npan * QB * QB, st));
+  tnb200_tensor_t dst;
+  dst.data = W; dst.dtype = a->dtype; dst.ndim = 2;
+  dst.shape[0] = m; dst.shape[1] = n; dst.stride[0] = 1; dst.stride[1] = m;
+  if ((rc = copy_strided(a, &dst, 0, st))) return rc;
+  const size_t apply_smem = sizeof(double) * (4 * QB * QLD + 2 * QB * (QB + 1));
+  static bool attr_done = false;
+  if (!attr_done) {
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(qr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
+    attr_done = true;
+  }
+  int launches = 0;
+  for (int p = 0; p < npan; ++p) {
+    const int j0 = p * QB, b = k - j0 < QB ? k - j0 : QB;
+    int rl = (int)((m - j0 + QCL - 1) / QCL);
+    if (rl < 1) rl = 1;
+    const size_t smem = sizeof(double) * ((size_t)QB * (rl + (rl & 1)) + 2 * QCL * 64 + 64 + 64 + QB + QB * (QB + 1)) + 16;
+    qr_panel_kernel<<<QCL, 256, smem, st>>>(W, m, j0, b, rl, tau + j0, Tb + (size_t)p * QB * QB, Z + (size_t)p * QB * QB);
+    ++launches;
+    if (j0 + b < n) {
+      const int nt = (int)(n - j0 - b);
+      qr_apply_kernel<<<(unsigned)((nt + QB - 1) / QB), 256, apply_smem, st>>>(W, m, j0, b, Tb + (size_t)p * QB * QB, 1, W, m, j0 + b, nt);
+      ++launches;
+    }
+  }
+  qr_init_q_kernel<double><<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Q, m, k);
+  for (int p = npan - 1; p >= 0; --p) {
+    const int j0 = p * QB, b = k - j0 < QB ? k - j0 : QB;
+    qr_apply_kernel<<<(unsigned)((k - j0 + QB - 1) / QB), 256, apply_smem, st>>>(W, m, j0, b, Tb + (size_t)p * QB * QB, 0, Q, m, j0, k - j0);
+    ++launches;
+  }
+  int64_t tot = m * k + (int64_t)k * n;
+  int64_t blocks = (tot + 255) / 256;
+  if (blocks > (int64_t)num_sms() * 16) blocks = (int64_t)num_sms() * 16;
+  qr_writeout_kernel<double><<<(unsigned)blocks, 256, 0, st>>>(W, Q, m, n, k, nonneg, (double*)q->data, q->stride[0], q->stride[1],
+                                                              (double*)r->data, r->stride[0], r->stride[1]);
+  TNB_LAUNCH_CHECK();
+  count_launch(launches + 2);
+  ws_free(W, st); ws_free(Q, st); ws_free(tau, st); ws_free(Tb, st); ws_free(Z, st);
+  return 0;
+}
+
 template <typename T>
 static int qr_real(const tnb200_tensor_t* a, const tnb200_tensor_t* q, const tnb200_tensor_t* r, int nonneg, cudaStream_t st) {
   const int64_t m = a->shape[0], n = a->shape[1];
@@ -142,7 +456,15 @@ extern "C" int32_t tnb200_qr(const tnb200_tensor_t* a, const tnb200_tensor_t* q,
   TNB_REQUIRE(m < (1LL << 31) && n < (1LL << 31), TNB200_ERR_UNSUPPORTED, "qr: matrix too large");
   set_kernel_name("qr_householder");
   cudaStream_t st = (cudaStream_t)stream;
-  if (a->dtype == TNB200_F64) return qr_real<double>(a, q, r, non_negative_diagonal, st);
+  if (a->dtype == TNB200_F64) {
+    // blocked path: the panel's rows must fit the shared memory of an 8-CTA cluster (m <= ~6500); TNB200_QR_ALGO=columns keeps the
+    // one-launch-per-column kernels
+    const char* algo = getenv("TNB200_QR_ALGO");
+    const int64_t rl = (m + QCL - 1) / QCL;
+    const bool fits = sizeof(double) * ((size_t)QB * (rl + 2) + 2 * QCL * 64 + 128 + QB + QB * (QB + 1)) + 16 <= 226 * 1024;
+    if (fits && k >= 16 && !(algo && !strcmp(algo, "columns"))) { set_kernel_name("qr_blocked_wy"); return qr_blocked_f64(a, q, r, non_negative_diagonal, st); }
+    return qr_real<double>(a, q, r, non_negative_diagonal, st);
+  }
   if (a->dtype == TNB200_C128) return qr_real<zd>(a, q, r, non_negative_diagonal, st);
   if (a->dtype == TNB200_F32 || a->dtype == TNB200_C64) {   // widen, factor, round back
     const bool cplx = a->dtype == TNB200_C64;
