@@ -31,6 +31,9 @@ struct DmmaParams {
   int64_t a_sm, a_sk, a_sb, b_sk, b_sn, b_sb, c_sm, c_sb;
   int64_t tiles_m, tiles_n;
   int vec_ok;
+  int ksplit;                 // > 1: the K range is cut into ksplit slices, slice s of a tile writes its partial product to
+  int64_t k_per;              //       ws[s][batch][M][N] (row-major); dmma_splitk_reduce_kernel sums them in slice order
+  double* ws;
 };
 
 // A_K: A tile stored [m][k] (K-major global operand) else [k][m]; B_K likewise ([n][k] / [k][n]).
@@ -47,6 +50,8 @@ __global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(const __grid_con
   double* Bs = dsm + DSTAGES * A_ELEMS;
 
   int64_t bid = blockIdx.x;
+  const int ks = p.ksplit > 1 ? (int)(bid % p.ksplit) : 0;
+  if (p.ksplit > 1) bid /= p.ksplit;
   const int64_t tn = bid % p.tiles_n; bid /= p.tiles_n;
   const int64_t tm = bid % p.tiles_m;
   const int64_t bb = bid / p.tiles_m;
@@ -55,10 +60,12 @@ __global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(const __grid_con
   const double* Bg = p.B + bb * p.b_sb;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = (warp >> 2) * 64, wn = (warp & 3) * WN;
-  const int num_kb = (int)((p.K + DBK - 1) / DBK);
+  const int64_t kbeg = p.ksplit > 1 ? (int64_t)ks * p.k_per : 0;
+  const int64_t kend = p.ksplit > 1 ? (kbeg + p.k_per < p.K ? kbeg + p.k_per : p.K) : p.K;
+  const int num_kb = kend > kbeg ? (int)((kend - kbeg + DBK - 1) / DBK) : 0;
 
   auto load_stage = [&](int stage, int kb) {
-    const int64_t k0 = (int64_t)kb * DBK;
+    const int64_t k0 = kbeg + (int64_t)kb * DBK;
     double* as = As + stage * A_ELEMS;
     double* bs = Bs + stage * B_ELEMS;
 #pragma unroll
@@ -66,7 +73,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(const __grid_con
       int idx = tid + i * DTHREADS;
       int m, k;
       if (A_K) { k = idx % DBK; m = idx / DBK; } else { m = idx % DBM; k = idx / DBM; }
-      bool ok = (m0 + m < p.M) && (k0 + k < p.K);
+      bool ok = (m0 + m < p.M) && (k0 + k < kend);
       const double* src = ok ? Ag + (m0 + m) * p.a_sm + (k0 + k) * p.a_sk : Ag;
       uint32_t dst = (uint32_t)__cvta_generic_to_shared(A_K ? as + m * A_LD + k : as + k * A_LD + m);
       cp_async8(dst, src, ok);
@@ -76,7 +83,7 @@ __global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(const __grid_con
       int idx = tid + i * DTHREADS;
       int n, k;
       if (B_K) { k = idx % DBK; n = idx / DBK; } else { n = idx % BN; k = idx / BN; }
-      bool ok = (n0 + n < p.N) && (k0 + k < p.K);
+      bool ok = (n0 + n < p.N) && (k0 + k < kend);
       const double* src = ok ? Bg + (n0 + n) * p.b_sn + (k0 + k) * p.b_sk : Bg;
       uint32_t dst = (uint32_t)__cvta_generic_to_shared(B_K ? bs + n * B_LD + k : bs + k * B_LD + n);
       cp_async8(dst, src, ok);
@@ -126,6 +133,21 @@ __global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(const __grid_con
   }
   cp_async_wait<0>();
 
+  if (p.ksplit > 1) {                      // partial product of this K slice: plain row-major [M][N] in the workspace
+    double* Wg = p.ws + (((int64_t)ks * p.batch + bb) * p.M) * p.N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int64_t m = m0 + wm + i * 8 + fr;
+      if (m >= p.M) continue;
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        int64_t n = n0 + wn + j * 8 + 2 * fk;
+        if (n < p.N) Wg[m * p.N + n] = acc[i][j][0];
+        if (n + 1 < p.N) Wg[m * p.N + n + 1] = acc[i][j][1];
+      }
+    }
+    return;
+  }
   double* Cg = p.C + bb * p.c_sb;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -142,6 +164,18 @@ __global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(const __grid_con
   }
 }
 
+// C[b][m][n] = sum over slices (in slice order: deterministic) of ws[s][b][m][n]
+__global__ void dmma_splitk_reduce_kernel(const double* __restrict__ ws, int ksplit, int64_t batch, int64_t M, int64_t N,
+                                          double* __restrict__ C, int64_t c_sm, int64_t c_sb) {
+  const int64_t total = batch * M * N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int s = 0; s < ksplit; ++s) acc += ws[(int64_t)s * total + idx];
+    const int64_t n = idx % N, m = (idx / N) % M, b = idx / (N * M);
+    C[b * c_sb + m * c_sm + n] = acc;
+  }
+}
+
 template <int BN, bool A_K, bool B_K>
 static int launch_dmma(const DmmaParams& p, int64_t tiles, cudaStream_t st) {
   constexpr int A_LD = A_K ? DBK + 4 : DBM + 4;
@@ -155,7 +189,7 @@ static int launch_dmma(const DmmaParams& p, int64_t tiles, cudaStream_t st) {
     if (e != cudaSuccess) { set_error("dmma: cannot raise dynamic smem: %s", cudaGetErrorString(e)); return TNB200_ERR_CUDA; }
     attr = true;
   }
-  gemm_dmma_kernel<BN, A_K, B_K><<<(unsigned)tiles, DTHREADS, smem, st>>>(p);
+  gemm_dmma_kernel<BN, A_K, B_K><<<(unsigned)(tiles * (p.ksplit > 1 ? p.ksplit : 1)), DTHREADS, smem, st>>>(p);
   TNB_LAUNCH_CHECK();
   count_launch();
   return 0;
@@ -179,17 +213,46 @@ int gemm_dmma_f64(const GemmProblem& g, cudaStream_t st) {
   p.tiles_n = (g.N + BN - 1) / BN;
   const int64_t tiles = p.tiles_m * p.tiles_n * g.batch;
   if (tiles >= (1LL << 31)) return TNB200_ERR_UNSUPPORTED;
+  // split-K: a small output under a long contraction (e.g. 64 x 64 over K = 65536, the closing step of a tree-network
+  // branch) would otherwise run on one SM.  Slices write partial products to a workspace, a second kernel sums them in
+  // slice order (deterministic, unlike atomics).
+  p.ksplit = 1; p.k_per = g.K; p.ws = nullptr;
+  if (tiles * 2 <= sms && g.K >= 2048) {
+    int64_t want = sms / tiles;
+    int64_t maxs = g.K / 512;                         // at least 512 of K per slice
+    if (want > maxs) want = maxs;
+    if (want > 1) {
+      p.k_per = ((g.K + want - 1) / want + DBK - 1) / DBK * DBK;
+      p.ksplit = (int)((g.K + p.k_per - 1) / p.k_per);
+      if (p.ksplit > 1) {
+        int rc = ws_alloc((void**)&p.ws, sizeof(double) * (size_t)p.ksplit * (size_t)g.batch * (size_t)g.M * (size_t)g.N, st);
+        if (rc) return rc;
+      } else { p.ksplit = 1; p.k_per = g.K; }
+    }
+  }
   // an operand is loaded "K-major" when its contracted stride is the smaller one
   const bool a_k = llabs(p.a_sk) <= llabs(p.a_sm) || g.M == 1;
   const bool b_k = llabs(p.b_sk) <= llabs(p.b_sn) || g.N == 1;
-  set_kernel_name("dmma_f64");
+  set_kernel_name(p.ksplit > 1 ? "dmma_f64_splitk" : "dmma_f64");
+  int rc;
 #define TNB_DMMA(BNV)                                                           \
-  if (a_k && b_k) return launch_dmma<BNV, true, true>(p, tiles, st);            \
-  if (a_k && !b_k) return launch_dmma<BNV, true, false>(p, tiles, st);          \
-  if (!a_k && b_k) return launch_dmma<BNV, false, true>(p, tiles, st);          \
-  return launch_dmma<BNV, false, false>(p, tiles, st);
+  if (a_k && b_k) rc = launch_dmma<BNV, true, true>(p, tiles, st);              \
+  else if (a_k && !b_k) rc = launch_dmma<BNV, true, false>(p, tiles, st);       \
+  else if (!a_k && b_k) rc = launch_dmma<BNV, false, true>(p, tiles, st);       \
+  else rc = launch_dmma<BNV, false, false>(p, tiles, st);
   if (BN == 128) { TNB_DMMA(128) } else { TNB_DMMA(64) }
 #undef TNB_DMMA
+  if (rc == 0 && p.ksplit > 1) {
+    const int64_t total = g.batch * g.M * g.N;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    dmma_splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(p.ws, p.ksplit, g.batch, g.M, g.N, p.C, p.c_sm, p.c_sb);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("dmma split-K reduce launch failed: %s", cudaGetErrorString(e)); rc = TNB200_ERR_CUDA; }
+    count_launch();
+  }
+  if (p.ws) ws_free(p.ws, st);
+  return rc;
 }
 
 }  // namespace tnb

@@ -1477,6 +1477,23 @@ int gemm_chain_create(int nsteps, const GemmProblem* probs, const int* dep_a, co
   const long long np = tile0 < pairs ? tile0 : pairs;
   h->grid = (unsigned)(2 * np);
   // two pairs per cluster sharing A by multicast when every step has an even number of N tiles and the grid is full
+  {
+    // every CTA pair of the launch must be resident (tiles wait on earlier tiles): ask the runtime how many 2-CTA clusters
+    // fit (MPS / green-context SM limits, other resident kernels) instead of assuming SMs / 2
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * np)); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = h->smem; cfg.stream = 0;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    cudaError_t qe = h->kind == 0 ? cudaFuncSetAttribute(gemm_tcgen05_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+                                  : cudaFuncSetAttribute(gemm_tcgen05_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (qe == cudaSuccess)
+      qe = h->kind == 0 ? cudaOccupancyMaxActiveClusters(&ncl, gemm_tcgen05_chain_kernel<0>, &cfg)
+                        : cudaOccupancyMaxActiveClusters(&ncl, gemm_tcgen05_chain_kernel<1>, &cfg);
+    if (qe != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+    if (ncl >= 1 && ncl < np) h->grid = (unsigned)(2 * ncl);
+  }
   h->cl = (cl4_ok && np == pairs && (pairs % 2) == 0 && (tile0 % 2) == 0) ? 4 : 2;
   if (h->cl == 4) {
     // every cluster must be resident (tiles wait on each other): a cluster lives inside one GPC, so fewer than SMs / 4

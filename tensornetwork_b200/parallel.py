@@ -51,7 +51,7 @@ def path_to_ssa(n_inputs, path):
   return out
 
 
-def partition_tree(n_inputs, path, step_flops, world, oversub=4):
+def partition_tree(n_inputs, path, step_flops, world, oversub=4, slack=0.03, tensor_bytes=None, small_bytes=1 << 20):
   """Assign every pairwise step of `path` to a rank.
 
   Returns (owner, transfers, info): owner[s] = rank executing SSA step s (in path order);
@@ -70,13 +70,30 @@ def partition_tree(n_inputs, path, step_flops, world, oversub=4):
     return cost[t]
   root = ssa[-1][2] if ssa else 0
   total = subtree_cost(root)
-  # grow a frontier of independent subtrees by repeatedly splitting the most expensive one
+  # Grow a frontier of independent subtrees by repeatedly splitting the most expensive one — but only as far as balance
+  # needs it: the coarsest frontier whose longest-processing-time-first packing is within `slack` of total / world keeps
+  # subtrees that are contracted with each other (a ket half and its bra half) on ONE rank, so what crosses NVLink at the
+  # joins are the small results above them rather than the large halves.  Fall back to world * oversub subtrees.
+  def lpt(front):
+    load = [0.0] * world
+    where = {}
+    for t in sorted(front, key=subtree_cost, reverse=True):
+      r = int(np.argmin(load))
+      load[r] += subtree_cost(t)
+      where[t] = r
+    return load, where
   frontier = [root]
   target = max(1, world * oversub)
   def splittable(t):
     a, b, _ = ssa[producer[t]]
     return a >= n_inputs or b >= n_inputs       # a step on two inputs is a leaf of the cut
-  while len(frontier) < target:
+  ideal = total / world if world else total
+  while True:
+    load, tensor_rank = lpt(frontier)
+    if len(frontier) >= world and max(load) <= (1.0 + slack) * ideal:
+      break
+    if len(frontier) >= target:
+      break
     cand = [t for t in frontier if t >= n_inputs and splittable(t)]
     if not cand:
       break
@@ -86,13 +103,7 @@ def partition_tree(n_inputs, path, step_flops, world, oversub=4):
     a, b, _ = ssa[producer[t]]
     frontier.remove(t)
     frontier.extend([x for x in (a, b) if x >= n_inputs])   # inputs live on every rank
-  # longest-processing-time-first packing of the frontier subtrees
-  load = [0.0] * world
-  tensor_rank = {}
-  for t in sorted(frontier, key=subtree_cost, reverse=True):
-    r = int(np.argmin(load))
-    load[r] += subtree_cost(t)
-    tensor_rank[t] = r
+  load, tensor_rank = lpt(frontier)
 
   owner = [None] * len(ssa)
 
@@ -106,9 +117,10 @@ def partition_tree(n_inputs, path, step_flops, world, oversub=4):
     assign_subtree(b, r)
   for t, r in tensor_rank.items():
     assign_subtree(t, r)
-  # steps above the cut: run where the larger-cost operand already lives
+  # steps above the cut: run where the larger-cost operand already lives; steps on small operands all run on `join_rank`
   transfers = []
   where = dict(tensor_rank)
+  join_rank = int(np.argmin(load))
 
   def locate(t):
     if t in where:
@@ -121,8 +133,13 @@ def partition_tree(n_inputs, path, step_flops, world, oversub=4):
       return owner[s]
     a, b, _ = ssa[s]
     ra, rb = locate(a), locate(b)
+    small = tensor_bytes is not None and all(tensor_bytes.get(x, 0) <= small_bytes for x in (a, b) if x >= n_inputs)
     if ra is None and rb is None:
-      r = int(np.argmin(load))
+      r = join_rank if small else int(np.argmin(load))
+    elif small:
+      # both operands are small: gather on ONE rank (a single hop from every producer) instead of a log-depth tree of
+      # hops — the joins above the cut are latency, not bandwidth
+      r = join_rank
     elif ra is None:
       r = rb
     elif rb is None:
@@ -338,7 +355,8 @@ class ShardedNetwork:
   result consumed on another rank is sent once, point to point (NCCL isend over NVLink) the moment it exists, into a
   receive the consumer posted before its first contraction.  No collective on the data path."""
 
-  def __init__(self, backend, shapes, dtype, labels, path, rank, world, group=None):
+  def __init__(self, backend, shapes, dtype, labels, path, rank, world, group=None, gather_joins=False, early_recv=False,
+               join_graphs=True):
     from . import drivers  # pylint: disable=import-outside-toplevel
     from . import tensor as T  # pylint: disable=import-outside-toplevel
     self.backend, self.rank, self.world, self.group = backend, rank, world, group
@@ -354,7 +372,13 @@ class ShardedNetwork:
       k = float(np.prod([sizes[l] for l in shared])) if shared else 1.0
       flops.append(2.0 * k * float(np.prod([sizes[l] for l in lab[o]] or [1.0])))
     self.step_flops = flops
-    self.owner, self.transfers, self.info = partition_tree(n, path, flops, world)
+    esz = 8 if T.dtype_code(dtype) in (0, 4, 7) else (16 if T.dtype_code(dtype) == 5 else 4)
+    tensor_bytes = {t: int(np.prod([sizes[l] for l in lab[t]] or [1])) * esz for t in lab}
+    # gather_joins: every step on small operands runs on one rank (single hop) instead of the default tree of joins;
+    # early_recv: receives posted before the first contraction (the NCCL receive kernels then sit on the GPU while it
+    # computes) instead of right before the join; join_graphs: runs of steps above the cut replayed as CUDA graphs
+    self.early_recv, self.join_graphs = early_recv, join_graphs
+    self.owner, self.transfers, self.info = partition_tree(n, path, flops, world, tensor_bytes=tensor_bytes if gather_joins else None)
     self.producer = {o: i for i, (_, _, o) in enumerate(ssa)}
     self.roots, self.pure = local_subtrees(n, ssa, self.owner, rank)
     self.code = T.dtype_code(dtype)
@@ -370,6 +394,26 @@ class ShardedNetwork:
       if rank == dst:
         self.incoming.append((self.producer.get(t, -1), t, src))
     self.incoming.sort()
+    # persistent receive buffers (static addresses: the steps above the cut are replayed as CUDA graphs)
+    self._recv = {t: backend._new([sizes[l] for l in lab[t]], self.code) for _, t, _ in self.incoming}  # pylint: disable=protected-access
+    # this rank's program above the cut: maximal runs of steps between two receives ("segments")
+    arriving = {t for _, t, _ in self.incoming}
+    self._segments, cur, have = [], [], set()
+    for s_i, (a_, b_, o_) in enumerate(ssa):
+      if self.owner[s_i] != rank or s_i in self.pure:
+        continue
+      need = [x for x in (a_, b_) if x in arriving and x not in have]
+      if need and cur:
+        self._segments.append(("steps", cur))
+        cur = []
+      for x in need:
+        self._segments.append(("recv", x))
+        have.add(x)
+      cur.append(s_i)
+    if cur:
+      self._segments.append(("steps", cur))
+    self._seg_graphs = {}
+    self._runs = 0
     self.inputs = None
     self.p2p_bytes = 0
 
@@ -388,15 +432,22 @@ class ShardedNetwork:
 
   def run(self):
     """-> (result B200Tensor on the root rank / None elsewhere, root_rank).  Stream-ordered; nothing blocks the host
-    except NCCL's own enqueue."""
+    except NCCL's own enqueue.  From the second call on, every run of steps above the cut is ONE CUDA-graph replay
+    (captured on static buffers: subtree outputs, persistent receive buffers, the inputs)."""
     import torch.distributed as dist  # pylint: disable=import-outside-toplevel
     be, rank, lab = self.backend, self.rank, self.lab
+    torch = be.torch
     handles, keep = {}, []
     moved = 0
-    for _, t, src in self.incoming:
-      buf = be._new([self.sizes[l] for l in lab[t]], self.code)  # pylint: disable=protected-access
-      handles[t] = (buf, dist.irecv(buf.t, src, group=self.group))
-      moved += buf.t.numel() * buf.t.element_size()
+
+    def post_receives():
+      nonlocal moved
+      for _, t, src in self.incoming:
+        buf = self._recv[t]
+        handles[t] = dist.irecv(buf.t, src, group=self.group)
+        moved += buf.t.numel() * buf.t.element_size()
+    if self.early_recv:
+      post_receives()
     vals = {}
 
     def emit(o, tensor):
@@ -408,22 +459,43 @@ class ShardedNetwork:
         keep.append((buf, dist.isend(buf.t, dst, group=self.group)))
     for root, (_, net) in self.nets.items():
       emit(root, net())
+    if not self.early_recv:
+      post_receives()       # after the local subtrees are enqueued: NCCL orders its stream behind them, the receive
+                            # kernels do not occupy the GPU while it computes
 
     def get(x):
-      if x < self.n:
-        return self.inputs[x]
-      if x not in vals and x in handles:
-        buf, work = handles.pop(x)
-        work.wait()                      # the compute stream waits for the transfer; the host does not
-        vals[x] = buf
-      return vals[x]
-    for s, (a, b, o) in enumerate(self.ssa):
-      if self.owner[s] != rank or s in self.pure:
+      return self.inputs[x] if x < self.n else vals[x]
+
+    def run_steps(steps):
+      out = {}
+      for s_i in steps:
+        a_, b_, o_ = self.ssa[s_i]
+        vals[o_] = out[o_] = self._pair(get(a_), lab[a_], get(b_), lab[b_])
+      return out
+    for k, (kind, what) in enumerate(self._segments):
+      if kind == "recv":
+        handles.pop(what).wait()           # the compute stream waits for the transfer; the host does not
+        vals[what] = self._recv[what]
         continue
-      emit(o, self._pair(get(a), lab[a], get(b), lab[b]))
+      if k in self._seg_graphs:
+        graph, outs = self._seg_graphs[k]
+        graph.replay()
+        vals.update(outs)
+      elif self._runs >= 1 and self.join_graphs:
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.current_stream().synchronize()
+        with torch.cuda.graph(graph):
+          outs = run_steps(what)
+        self._seg_graphs[k] = (graph, outs)
+        graph.replay()
+      else:
+        outs = run_steps(what)
+      for o_ in outs:
+        emit(o_, vals[o_])
     for _, w in keep:
       w.wait()
     self._keep = keep
+    self._runs += 1
     self.p2p_bytes = moved
     root_rank = self.owner[-1] if self.ssa else 0
     res = vals.get(self.ssa[-1][2]) if (self.ssa and rank == root_rank) else None

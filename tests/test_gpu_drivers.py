@@ -268,3 +268,38 @@ def test_cfg2_full_size_fp64_vs_oracle_and_scaling_property():
     tb_ = [d.to_host()[b].astype(np.float64) for d in dev]
     ex = nn.contract_path(tb_ + [np.conj(t) for t in tb_], labels, path, [])
     assert abs(base[b] - ex) <= 3e-2 * abs(ex), (b, base[b], ex)
+
+
+def test_sharded_network_single_rank_equals_oracle():
+  """parallel.ShardedNetwork with world = 1 (no transfers): the whole tree is one local subtree replayed as a CUDA graph;
+  result equals the numpy oracle along the same path (fp64, 1e-10).  The N > 1 schedule is exercised by the gloo tests
+  (host logic) and by `bench.py --gpus N` (`strong_scaling.parity_ok`)."""
+  import sys, os
+  sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+  import bench
+  from tensornetwork_b200 import drivers, parallel
+  be = get_backend()
+  labels, sizes, shapes, dims = bench.ttn_network({"b3": 48, "b2": 12, "b1": 6, "p": 4})
+  path = drivers.greedy_path(labels, [], sizes)
+  rng = np.random.default_rng(9)
+  n_ket = len(labels) // 2
+  kets = [rng.standard_normal(shapes[i]) / np.sqrt(np.prod(shapes[i][1:])) for i in range(n_ket)]
+  host = kets + [np.conj(k) for k in kets]
+  ref = float(nn.contract_path(host, labels, path, []))
+  sh = parallel.ShardedNetwork(be, shapes, np.float64, labels, path, 0, 1)
+  sh.load([be.convert_to_tensor(h) for h in host])
+  for _ in range(2):
+    out, root = sh.run()
+  assert root == 0 and abs(float(out.to_host()) - ref) <= 1e-10 * abs(ref)
+  # the partition used at N = 4 keeps a ket half and its bra half on one rank: only small tensors cross ranks
+  labels_f, sizes_f, shapes_f, _ = bench.ttn_network(None)          # the benchmark's dimensions, symbolically
+  path_f = drivers.greedy_path(labels_f, [], sizes_f)
+  flops_f = [2.0 * m * k * n_ for m, k, n_ in nn.network_flops(labels_f, path_f, sizes_f)]
+  owner, transfers, info = parallel.partition_tree(len(labels_f), path_f, flops_f, 4)
+  ssa = parallel.path_to_ssa(len(labels_f), path_f)
+  lab = {i: list(l) for i, l in enumerate(labels_f)}
+  for a, b, o in ssa:
+    shared = [l for l in lab[a] if l in lab[b]]
+    lab[o] = [l for l in lab[a] if l not in shared] + [l for l in lab[b] if l not in shared]
+  biggest = max(int(np.prod([sizes_f[l] for l in lab[t]])) for t, _, _, _ in transfers)
+  assert biggest <= 64 * 64 * 16 and max(info["per_rank"]) <= 1.05 * info["total"] / 4

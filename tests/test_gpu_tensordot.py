@@ -3,7 +3,7 @@ reference and vs the numpy oracle on seeded inputs."""
 import numpy as np
 import pytest
 from conftest import load_golden
-from util import assert_close, get_backend, TOL
+from util import assert_close, get_backend, rel_err, TOL
 from oracle import np_backend as nb
 
 pytestmark = pytest.mark.gpu
@@ -181,3 +181,25 @@ def test_skinny_outer_family(dtype):
   out = be._contract(be.convert_to_tensor(A), be.convert_to_tensor(B), [2], [2], [0], [0])
   assert be.lib.tnb200_last_kernel().decode() == "skinny_outer"
   assert_close(out, np.einsum("bmk,bnk->bmn", A.astype(np.float64), B.astype(np.float64)), tol=tol)
+
+
+@pytest.mark.parametrize("shape_a,shape_b,axes", [
+    ((16, 16, 64, 16, 16), (16, 16, 48, 16, 16), ([0, 1, 3, 4], [0, 1, 3, 4])),     # 64 x 48 output over K = 65536
+    ((40000, 24), (40000, 8), ([0], [0])),                                          # tall operands, tiny output
+    ((3, 20, 9000), (3, 9000, 12), None),                                           # batched matmul with long K
+])
+def test_fp64_split_k(shape_a, shape_b, axes):
+  """fp64 DMMA with a small output under a long contraction: K is cut into slices whose partial products are summed in slice
+  order by a second kernel (deterministic); result against numpy at 1e-12, and bit-identical between two runs."""
+  be = get_backend()
+  rng = np.random.default_rng(12)
+  a, b = rng.standard_normal(shape_a), rng.standard_normal(shape_b)
+  A, B = be.convert_to_tensor(a), be.convert_to_tensor(b)
+  if axes is None:
+    got1, got2, ref = be.matmul(A, B).to_host(), be.matmul(A, B).to_host(), np.matmul(a, b)
+  else:
+    got1, got2 = be.tensordot(A, B, axes).to_host(), be.tensordot(A, B, axes).to_host()
+    ref = np.tensordot(a, b, axes)
+  assert be.lib.tnb200_last_kernel().decode() == "dmma_f64_splitk"
+  assert rel_err(got1, ref) < 1e-12
+  np.testing.assert_array_equal(got1, got2)
