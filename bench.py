@@ -775,7 +775,7 @@ def collect_subrecords(args):
                       ("flagship_batched64_bf16", ["--config", "flagship64", "--dtype", "bf16", "--steps", "10"]),
                       ("cfg3_split_svd_4096_f64", ["--config", "cfg3", "--dtype", "f64", "--steps", "2"]),
                       ("cfg4_blocksparse_f64", ["--config", "cfg4", "--dtype", "f64", "--steps", "20"]),
-                      ("cfg5_dmrg_site_D1024_f64", ["--config", "cfg5", "--dtype", "f64", "--steps", "2"])):
+                      ("cfg5_dmrg_site_D1024_f64", ["--config", "cfg5", "--dtype", "f64", "--steps", "4"])):
     d = _run_sub(extra)
     if "error" in d:
       out["configs"][name] = d
@@ -1146,7 +1146,8 @@ def run_config(args):
     # inputs for the same number of updates; only the backend differs ("cuda_b200" vs "numpy").
     D = int(os.environ.get("TNB200_CFG5_D", "1024"))
     lo = int(np.ceil(np.log2(D)))
-    nup = max(2, min(steps, 4))                           # timed updates per arm (the GPU arm does one more, untimed, first)
+    nup = max(2, min(steps, 4))                           # timed updates on the GPU arm (it does one more, untimed, first; the
+                                                          # second one also records the CUDA graphs of the jitted ncon calls)
     N = 2 * lo + 2 + nup + 1
     rng = np.random.default_rng(6)
     dims = [min(D, 2**min(i, N - i)) for i in range(N + 1)]

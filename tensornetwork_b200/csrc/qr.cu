@@ -244,93 +244,116 @@ qr_panel_kernel(double* __restrict__ W, int64_t m, int j0, int b, int rl, double
   }
 }
 
-// X[j0:, c0 + 32 blockIdx.x ...] <- (I - V T' V^T) X ; V = unit lower trapezoid stored in W[j0:, j0:j0+b], T' = transT ? T^T : T
-__global__ void __launch_bounds__(256) qr_apply_kernel(const double* __restrict__ W, int64_t m, int j0, int b, const double* __restrict__ T,
-                                                       int transT, double* __restrict__ X, int64_t ldx, int c0, int ncols) {
+// X[j0:, c0 + 32 blockIdx.x ...] <- (I - V T' V^T) X ; V = unit lower trapezoid stored in W[j0:, j0:j0+b], T' = transT ? T^T : T.
+// Two kernels over a (column block, row chunk) grid so that a narrow trailing matrix still fills the GPU:
+//   qr_apply1_kernel : partial W1 = V^T X over this chunk's row tiles -> w1p[column block][chunk][32 x 32]
+//   qr_apply2_kernel : W1 = sum of the partials in chunk order (deterministic), W2 = T' W1, X -= V W2 on this chunk's rows
+struct QrApply {
+  const double* W; int64_t m; int j0, b; const double* T; int transT; double* X; int64_t ldx; int c0, ncols; int rs; double* w1p;
+};
+__device__ __forceinline__ void qr_fetch_tile(const QrApply& q, int cb, int nc, int t, int e_c, int e_r, double* pv, double* px) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = e_r + 8 * i;
+    const int64_t gi = (int64_t)q.j0 + (int64_t)t * 64 + r;
+    double v = 0.0, x = 0.0;
+    if (gi < q.m) {
+      if (e_c < q.b) {
+        const int64_t piv = (int64_t)q.j0 + e_c;
+        v = gi > piv ? q.W[(int64_t)(q.j0 + e_c) * q.m + gi] : (gi == piv ? 1.0 : 0.0);
+      }
+      if (e_c < nc) x = q.X[(int64_t)(cb + e_c) * q.ldx + gi];
+    }
+    pv[i] = v; px[i] = x;
+  }
+}
+
+__global__ void __launch_bounds__(256) qr_apply1_kernel(const QrApply q) {
   extern __shared__ __align__(16) double qasm[];
-  double (*tv)[QB * QLD] = reinterpret_cast<double (*)[QB * QLD]>(qasm);                      // V tile  [2][k][row]
-  double (*tx)[QB * QLD] = reinterpret_cast<double (*)[QB * QLD]>(qasm + 2 * QB * QLD);       // X tile  [2][c][row]
+  double (*tv)[QB * QLD] = reinterpret_cast<double (*)[QB * QLD]>(qasm);
+  double (*tx)[QB * QLD] = reinterpret_cast<double (*)[QB * QLD]>(qasm + 2 * QB * QLD);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fk = lane & 3;
+  const int cb = q.c0 + blockIdx.x * QB;
+  const int nc = q.ncols - blockIdx.x * QB < QB ? q.ncols - blockIdx.x * QB : QB;
+  const int ntiles = (int)((q.m - q.j0 + 63) / 64);
+  const int t0 = (int)((int64_t)ntiles * blockIdx.y / q.rs), t1 = (int)((int64_t)ntiles * (blockIdx.y + 1) / q.rs);
+  const int e_c = tid >> 3, e_r = tid & 7;
+  double pv[8], px[8];
+  const int mt = warp >> 1, nt0 = (warp & 1) * 2;
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+  if (t0 < t1) {
+    qr_fetch_tile(q, cb, nc, t0, e_c, e_r, pv, px);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tv[0][e_c * QLD + e_r + 8 * i] = pv[i]; tx[0][e_c * QLD + e_r + 8 * i] = px[i]; }
+    __syncthreads();
+    int buf = 0;
+    for (int t = t0; t < t1; ++t) {
+      if (t + 1 < t1) qr_fetch_tile(q, cb, nc, t + 1, e_c, e_r, pv, px);
+      const double* av = tv[buf];
+      const double* bx = tx[buf];
+#pragma unroll
+      for (int k4 = 0; k4 < 64; k4 += 4) {
+        const double a = av[(mt * 8 + fr) * QLD + k4 + fk];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) qr_dmma(acc[j][0], acc[j][1], a, bx[((nt0 + j) * 8 + fr) * QLD + k4 + fk]);
+      }
+      if (t + 1 < t1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { tv[buf ^ 1][e_c * QLD + e_r + 8 * i] = pv[i]; tx[buf ^ 1][e_c * QLD + e_r + 8 * i] = px[i]; }
+      }
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  double* out = q.w1p + ((size_t)blockIdx.x * q.rs + blockIdx.y) * (QB * QB);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    out[(mt * 8 + fr) * QB + (nt0 + j) * 8 + 2 * fk] = acc[j][0];
+    out[(mt * 8 + fr) * QB + (nt0 + j) * 8 + 2 * fk + 1] = acc[j][1];
+  }
+}
+
+__global__ void __launch_bounds__(256) qr_apply2_kernel(const QrApply q) {
+  extern __shared__ __align__(16) double qasm[];
+  double (*tv)[QB * QLD] = reinterpret_cast<double (*)[QB * QLD]>(qasm);
+  double (*tx)[QB * QLD] = reinterpret_cast<double (*)[QB * QLD]>(qasm + 2 * QB * QLD);
   double* w1 = qasm + 4 * QB * QLD;
   double* w2 = w1 + QB * (QB + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, fr = lane >> 2, fk = lane & 3;
-  const int cb = c0 + blockIdx.x * QB;
-  const int nc = ncols - blockIdx.x * QB < QB ? ncols - blockIdx.x * QB : QB;
-  const int64_t R = m - j0;
-  const int ntiles = (int)((R + 63) / 64);
-  // element (col e_c, rows e_r + 8 i) of a 32 x 64 tile for this thread: 8 elements per operand
-  const int e_c = tid >> 3, e_r = tid & 7;
-  double pv[8], px[8];
-  auto fetch = [&](int t) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = e_r + 8 * i;
-      const int64_t gi = (int64_t)j0 + (int64_t)t * 64 + r;
-      double v = 0.0, x = 0.0;
-      if (gi < m) {
-        if (e_c < b) {
-          const int64_t piv = (int64_t)j0 + e_c;
-          v = gi > piv ? W[(int64_t)(j0 + e_c) * m + gi] : (gi == piv ? 1.0 : 0.0);
-        }
-        if (e_c < nc) x = X[(int64_t)(cb + e_c) * ldx + gi];
-      }
-      pv[i] = v; px[i] = x;
-    }
-  };
-  auto stash = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { tv[buf][e_c * QLD + e_r + 8 * i] = pv[i]; tx[buf][e_c * QLD + e_r + 8 * i] = px[i]; }
-  };
-  // ---- pass 1: W1[k][c] = sum_rows V[row][k] X[row][c]      (16 output tiles of 8 x 8, two per warp)
-  const int mt = warp >> 1, nt0 = (warp & 1) * 2;
-  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-  fetch(0);
-  stash(0);
-  __syncthreads();
-  int buf = 0;
-  for (int t = 0; t < ntiles; ++t) {
-    if (t + 1 < ntiles) fetch(t + 1);
-    const double* av = tv[buf];
-    const double* bx = tx[buf];
-#pragma unroll
-    for (int k4 = 0; k4 < 64; k4 += 4) {
-      const double a = av[(mt * 8 + fr) * QLD + k4 + fk];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) qr_dmma(acc[j][0], acc[j][1], a, bx[((nt0 + j) * 8 + fr) * QLD + k4 + fk]);
-    }
-    if (t + 1 < ntiles) stash(buf ^ 1);
-    __syncthreads();
-    buf ^= 1;
-  }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    w1[(mt * 8 + fr) * (QB + 1) + (nt0 + j) * 8 + 2 * fk] = acc[j][0];
-    w1[(mt * 8 + fr) * (QB + 1) + (nt0 + j) * 8 + 2 * fk + 1] = acc[j][1];
+  const int cb = q.c0 + blockIdx.x * QB;
+  const int nc = q.ncols - blockIdx.x * QB < QB ? q.ncols - blockIdx.x * QB : QB;
+  const int ntiles = (int)((q.m - q.j0 + 63) / 64);
+  const int t0 = (int)((int64_t)ntiles * blockIdx.y / q.rs), t1 = (int)((int64_t)ntiles * (blockIdx.y + 1) / q.rs);
+  if (t0 >= t1) return;
+  const double* part = q.w1p + (size_t)blockIdx.x * q.rs * (QB * QB);
+  for (int idx = tid; idx < QB * QB; idx += 256) {
+    double s = 0.0;
+    for (int c = 0; c < q.rs; ++c) s += part[(size_t)c * (QB * QB) + idx];
+    w1[(idx >> 5) * (QB + 1) + (idx & 31)] = s;
   }
   __syncthreads();
-  // ---- W2 = T' W1
   for (int idx = tid; idx < QB * QB; idx += 256) {
     const int k = idx >> 5, c = idx & 31;
     double s = 0.0;
-    if (k < b) {
-      for (int l = 0; l < b; ++l) {
-        const double tkl = transT ? T[l * QB + k] : T[k * QB + l];
-        s = fma(tkl, w1[l * (QB + 1) + c], s);
-      }
+    if (k < q.b) {
+      for (int l = 0; l < q.b; ++l) s = fma(q.transT ? q.T[l * QB + k] : q.T[k * QB + l], w1[l * (QB + 1) + c], s);
     }
     w2[k * (QB + 1) + c] = s;
   }
   __syncthreads();
-  // ---- pass 2: X^T[c][row] -= sum_k W2[k][c] V^T[k][row]     (warp: 8 columns x 32 rows of every tile)
+  const int e_c = tid >> 3, e_r = tid & 7;
+  double pv[8], px[8];
   const int ct = warp >> 1, rh = (warp & 1) * 32;
   double wa[8];
 #pragma unroll
   for (int k4 = 0; k4 < 8; ++k4) wa[k4] = w2[(k4 * 4 + fk) * (QB + 1) + ct * 8 + fr];
-  fetch(0);
-  stash(0);
+  qr_fetch_tile(q, cb, nc, t0, e_c, e_r, pv, px);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { tv[0][e_c * QLD + e_r + 8 * i] = pv[i]; tx[0][e_c * QLD + e_r + 8 * i] = px[i]; }
   __syncthreads();
-  buf = 0;
-  for (int t = 0; t < ntiles; ++t) {
-    if (t + 1 < ntiles) fetch(t + 1);
+  int buf = 0;
+  for (int t = t0; t < t1; ++t) {
+    if (t + 1 < t1) qr_fetch_tile(q, cb, nc, t + 1, e_c, e_r, pv, px);
     const double* av = tv[buf];
     double oc[4][2];
 #pragma unroll
@@ -344,16 +367,35 @@ __global__ void __launch_bounds__(256) qr_apply_kernel(const double* __restrict_
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = rh + j * 8 + 2 * fk;
-        const int64_t gi = (int64_t)j0 + (int64_t)t * 64 + r;
-        double* dst = X + (int64_t)(cb + c) * ldx + gi;
-        if (gi < m) dst[0] = tx[buf][c * QLD + r] - oc[j][0];
-        if (gi + 1 < m) dst[1] = tx[buf][c * QLD + r + 1] - oc[j][1];
+        const int64_t gi = (int64_t)q.j0 + (int64_t)t * 64 + r;
+        double* dst = q.X + (int64_t)(cb + c) * q.ldx + gi;
+        if (gi < q.m) dst[0] = tx[buf][c * QLD + r] - oc[j][0];
+        if (gi + 1 < q.m) dst[1] = tx[buf][c * QLD + r + 1] - oc[j][1];
       }
     }
-    if (t + 1 < ntiles) stash(buf ^ 1);
+    if (t + 1 < t1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { tv[buf ^ 1][e_c * QLD + e_r + 8 * i] = pv[i]; tx[buf ^ 1][e_c * QLD + e_r + 8 * i] = px[i]; }
+    }
     __syncthreads();
     buf ^= 1;
   }
+}
+
+static int qr_apply(const QrApply& q0, double* w1p, size_t w1p_doubles, cudaStream_t st, int* launches) {
+  QrApply q = q0;
+  const int ncb = (q.ncols + QB - 1) / QB;
+  const int ntiles = (int)((q.m - q.j0 + 63) / 64);
+  int rs = (2 * num_sms() + ncb - 1) / ncb;
+  if (rs > ntiles) rs = ntiles;
+  if (rs < 1) rs = 1;
+  while ((size_t)ncb * rs * QB * QB > w1p_doubles && rs > 1) --rs;
+  q.rs = rs; q.w1p = w1p;
+  const size_t smem1 = sizeof(double) * (4 * QB * QLD), smem2 = sizeof(double) * (4 * QB * QLD + 2 * QB * (QB + 1));
+  qr_apply1_kernel<<<dim3((unsigned)ncb, (unsigned)rs), 256, smem1, st>>>(q);
+  qr_apply2_kernel<<<dim3((unsigned)ncb, (unsigned)rs), 256, smem2, st>>>(q);
+  *launches += 2;
+  return 0;
 }
 
 static int qr_blocked_f64(const tnb200_tensor_t* a, const tnb200_tensor_t* q, const tnb200_tensor_t* r, int nonneg, cudaStream_t st) {
@@ -376,9 +418,14 @@ static int qr_blocked_f64(const tnb200_tensor_t* a, const tnb200_tensor_t* q, co
   static bool attr_done = false;
   if (!attr_done) {
     TNB_CHECK_CUDA(cudaFuncSetAttribute(qr_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-    TNB_CHECK_CUDA(cudaFuncSetAttribute(qr_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(qr_apply1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
+    TNB_CHECK_CUDA(cudaFuncSetAttribute(qr_apply2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
     attr_done = true;
   }
+  // partial W1 blocks of the apply kernels: (column blocks) x (row chunks) x 32 x 32, at most ~2 CTAs per SM worth of chunks
+  const size_t w1p_doubles = (size_t)(2 * num_sms() + (n + QB - 1) / QB + 8) * QB * QB;
+  double* w1p = nullptr;
+  if ((rc = ws_alloc((void**)&w1p, sizeof(double) * w1p_doubles, st))) return rc;
   int launches = 0;
   for (int p = 0; p < npan; ++p) {
     const int j0 = p * QB, b = k - j0 < QB ? k - j0 : QB;
@@ -388,16 +435,15 @@ static int qr_blocked_f64(const tnb200_tensor_t* a, const tnb200_tensor_t* q, co
     qr_panel_kernel<<<QCL, 256, smem, st>>>(W, m, j0, b, rl, tau + j0, Tb + (size_t)p * QB * QB, Z + (size_t)p * QB * QB);
     ++launches;
     if (j0 + b < n) {
-      const int nt = (int)(n - j0 - b);
-      qr_apply_kernel<<<(unsigned)((nt + QB - 1) / QB), 256, apply_smem, st>>>(W, m, j0, b, Tb + (size_t)p * QB * QB, 1, W, m, j0 + b, nt);
-      ++launches;
+      QrApply q{W, m, j0, b, Tb + (size_t)p * QB * QB, 1, W, m, j0 + b, (int)(n - j0 - b), 1, nullptr};
+      qr_apply(q, w1p, w1p_doubles, st, &launches);
     }
   }
   qr_init_q_kernel<double><<<(unsigned)((m * k + 255) / 256), 256, 0, st>>>(Q, m, k);
   for (int p = npan - 1; p >= 0; --p) {
     const int j0 = p * QB, b = k - j0 < QB ? k - j0 : QB;
-    qr_apply_kernel<<<(unsigned)((k - j0 + QB - 1) / QB), 256, apply_smem, st>>>(W, m, j0, b, Tb + (size_t)p * QB * QB, 0, Q, m, j0, k - j0);
-    ++launches;
+    QrApply q{W, m, j0, b, Tb + (size_t)p * QB * QB, 0, Q, m, j0, k - j0, 1, nullptr};
+    qr_apply(q, w1p, w1p_doubles, st, &launches);
   }
   int64_t tot = m * k + (int64_t)k * n;
   int64_t blocks = (tot + 255) / 256;
@@ -406,7 +452,7 @@ static int qr_blocked_f64(const tnb200_tensor_t* a, const tnb200_tensor_t* q, co
                                                               (double*)r->data, r->stride[0], r->stride[1]);
   TNB_LAUNCH_CHECK();
   count_launch(launches + 2);
-  ws_free(W, st); ws_free(Q, st); ws_free(tau, st); ws_free(Tb, st); ws_free(Z, st);
+  ws_free(W, st); ws_free(Q, st); ws_free(tau, st); ws_free(Tb, st); ws_free(Z, st); ws_free(w1p, st);
   return 0;
 }
 

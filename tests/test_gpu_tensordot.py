@@ -187,10 +187,12 @@ def test_skinny_outer_family(dtype):
     ((16, 16, 64, 16, 16), (16, 16, 48, 16, 16), ([0, 1, 3, 4], [0, 1, 3, 4])),     # 64 x 48 output over K = 65536
     ((40000, 24), (40000, 8), ([0], [0])),                                          # tall operands, tiny output
     ((3, 20, 9000), (3, 9000, 12), None),                                           # batched matmul with long K
+    ((32768, 96), (32768, 160), ([0], [0])),                                        # 96 x 160 output: two DMMA tiles, K cut into slices
 ])
 def test_fp64_split_k(shape_a, shape_b, axes):
-  """fp64 DMMA with a small output under a long contraction: K is cut into slices whose partial products are summed in slice
-  order by a second kernel (deterministic); result against numpy at 1e-12, and bit-identical between two runs."""
+  """fp64, a small output under a long contraction: K is cut into slices whose partial products are summed in slice order by a
+  second kernel (deterministic) — the SIMT split-K kernel for outputs up to 64 x 64, the DMMA kernel with split-K above;
+  result against numpy at 1e-12, and bit-identical between two runs."""
   be = get_backend()
   rng = np.random.default_rng(12)
   a, b = rng.standard_normal(shape_a), rng.standard_normal(shape_b)
@@ -200,6 +202,7 @@ def test_fp64_split_k(shape_a, shape_b, axes):
   else:
     got1, got2 = be.tensordot(A, B, axes).to_host(), be.tensordot(A, B, axes).to_host()
     ref = np.tensordot(a, b, axes)
-  assert be.lib.tnb200_last_kernel().decode() == "dmma_f64_splitk"
+  kern = be.lib.tnb200_last_kernel().decode()
+  assert kern == ("dmma_f64_splitk" if min(ref.shape[-2:]) > 64 else "simt_splitk"), kern
   assert rel_err(got1, ref) < 1e-12
   np.testing.assert_array_equal(got1, got2)
