@@ -64,29 +64,40 @@ __global__ void __launch_bounds__(DTHREADS, 1) gemm_dmma_kernel(const __grid_con
   const int64_t kend = p.ksplit > 1 ? (kbeg + p.k_per < p.K ? kbeg + p.k_per : p.K) : p.K;
   const int num_kb = kend > kbeg ? (int)((kend - kbeg + DBK - 1) / DBK) : 0;
 
+  // Per-thread copy pattern, hoisted out of the k loop: element i of a stage differs from element 0 by a constant stride
+  // (rows 16 apart for a K-major tile, k-rows 2 apart for an MN-major one), so a stage costs one 64-bit add per cp.async
+  // instead of a multiply-add pair per element.
+  const int a_k = A_K ? tid % DBK : tid / DBM, a_m = A_K ? tid / DBK : tid % DBM;
+  const int b_k = B_K ? tid % DBK : tid / BN, b_n = B_K ? tid / DBK : tid % BN;
+  constexpr int A_IT = DBM * DBK / DTHREADS, B_IT = BN * DBK / DTHREADS;
+  constexpr int A_STEP = A_K ? DTHREADS / DBK : DTHREADS / DBM;     // rows (A_K) or k-rows (else) between consecutive elements
+  constexpr int B_STEP = B_K ? DTHREADS / DBK : DTHREADS / BN;
+  const double* pA0 = Ag + (m0 + a_m) * p.a_sm + (kbeg + a_k) * p.a_sk;
+  const double* pB0 = Bg + (n0 + b_n) * p.b_sn + (kbeg + b_k) * p.b_sk;
+  const int64_t a_inc = A_K ? (int64_t)A_STEP * p.a_sm : (int64_t)A_STEP * p.a_sk;
+  const int64_t b_inc = B_K ? (int64_t)B_STEP * p.b_sn : (int64_t)B_STEP * p.b_sk;
+  const int64_t a_mrem = p.M - m0 - a_m, b_nrem = p.N - n0 - b_n;    // > 0 iff this thread's (first) row / column exists
+  const uint32_t a_dst0 = (uint32_t)__cvta_generic_to_shared(A_K ? As + a_m * A_LD + a_k : As + a_k * A_LD + a_m);
+  const uint32_t b_dst0 = (uint32_t)__cvta_generic_to_shared(B_K ? Bs + b_n * B_LD + b_k : Bs + b_k * B_LD + b_n);
+  constexpr uint32_t A_DSTEP = (A_K ? A_STEP * A_LD : A_STEP * A_LD) * 8, B_DSTEP = (B_K ? B_STEP * B_LD : B_STEP * B_LD) * 8;
+
   auto load_stage = [&](int stage, int kb) {
     const int64_t k0 = kbeg + (int64_t)kb * DBK;
-    double* as = As + stage * A_ELEMS;
-    double* bs = Bs + stage * B_ELEMS;
+    const int64_t krem_a = kend - k0 - a_k, krem_b = kend - k0 - b_k;
+    const double* pa = pA0 + (int64_t)kb * DBK * p.a_sk;
+    const double* pb = pB0 + (int64_t)kb * DBK * p.b_sk;
+    uint32_t da = a_dst0 + (uint32_t)(stage * A_ELEMS * 8), db = b_dst0 + (uint32_t)(stage * B_ELEMS * 8);
 #pragma unroll
-    for (int i = 0; i < DBM * DBK / DTHREADS; ++i) {
-      int idx = tid + i * DTHREADS;
-      int m, k;
-      if (A_K) { k = idx % DBK; m = idx / DBK; } else { m = idx % DBM; k = idx / DBM; }
-      bool ok = (m0 + m < p.M) && (k0 + k < kend);
-      const double* src = ok ? Ag + (m0 + m) * p.a_sm + (k0 + k) * p.a_sk : Ag;
-      uint32_t dst = (uint32_t)__cvta_generic_to_shared(A_K ? as + m * A_LD + k : as + k * A_LD + m);
-      cp_async8(dst, src, ok);
+    for (int i = 0; i < A_IT; ++i) {
+      const bool ok = A_K ? (a_mrem > (int64_t)i * A_STEP && krem_a > 0) : (a_mrem > 0 && krem_a > (int64_t)i * A_STEP);
+      cp_async8(da, ok ? pa : Ag, ok);
+      pa += a_inc; da += A_DSTEP;
     }
 #pragma unroll
-    for (int i = 0; i < BN * DBK / DTHREADS; ++i) {
-      int idx = tid + i * DTHREADS;
-      int n, k;
-      if (B_K) { k = idx % DBK; n = idx / DBK; } else { n = idx % BN; k = idx / BN; }
-      bool ok = (n0 + n < p.N) && (k0 + k < kend);
-      const double* src = ok ? Bg + (n0 + n) * p.b_sn + (k0 + k) * p.b_sk : Bg;
-      uint32_t dst = (uint32_t)__cvta_generic_to_shared(B_K ? bs + n * B_LD + k : bs + k * B_LD + n);
-      cp_async8(dst, src, ok);
+    for (int i = 0; i < B_IT; ++i) {
+      const bool ok = B_K ? (b_nrem > (int64_t)i * B_STEP && krem_b > 0) : (b_nrem > 0 && krem_b > (int64_t)i * B_STEP);
+      cp_async8(db, ok ? pb : Bg, ok);
+      pb += b_inc; db += B_DSTEP;
     }
   };
 
