@@ -327,7 +327,8 @@ def main():
   import torch.distributed as dist
   if world > 1:
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # rank 0's stdout carries exactly one JSON line
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import datetime  # pylint: disable=import-outside-toplevel
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=240))
   torch.cuda.set_device(local)
   import tensornetwork_b200 as tb
   from tensornetwork_b200 import drivers, _lib
@@ -668,11 +669,13 @@ def strong_scaling_record(be, rank, world, dist, steps, b3=None):
     dist.barrier()
     return e0.elapsed_time(e1) / steps, out
   ms1, out1 = timed(single)
-  # the schedule knobs of ShardedNetwork, each measured (max over ranks); the fastest is the record's `ms_sharded`
-  variants = {"tree joins, late receives, join graphs": dict(),
-              "tree joins, late receives, eager joins": dict(join_graphs=False),
-              "tree joins, receives posted up front": dict(early_recv=True, join_graphs=False),
-              "joins gathered on one rank, late receives, join graphs": dict(gather_joins=True)}
+  # Schedule: tree of joins, receives posted right before they are needed, join steps eager.  Measured at 4 GPUs against the
+  # other ShardedNetwork knobs (graph-replayed join steps 3.840 ms, receives posted up front 3.905 ms, all small joins
+  # gathered on one rank 3.892 ms — all within 2 %): 3.839 ms (profiles/r2_BENCH_default_n4_v1.json).  One schedule only in
+  # the driver's run: the gathered plan DEADLOCKS at 8 GPUs (rank 0 sends a small tensor to rank 1 before it receives the
+  # large one from it, and with an eagerly initialised NCCL group a rank's point-to-point operations are serialised on one
+  # stream) and has been removed from ShardedNetwork.
+  variants = {"tree joins, late receives, eager joins": dict(join_graphs=False)}
   var_ms, best = {}, None
   for name, kw in variants.items():
     shv = parallel.ShardedNetwork(be, shapes, np.float64, labels, path, rank, world, **kw)

@@ -374,7 +374,14 @@ class ShardedNetwork:
     self.step_flops = flops
     esz = 8 if T.dtype_code(dtype) in (0, 4, 7) else (16 if T.dtype_code(dtype) == 5 else 4)
     tensor_bytes = {t: int(np.prod([sizes[l] for l in lab[t]] or [1])) * esz for t in lab}
-    # gather_joins: every step on small operands runs on one rank (single hop) instead of the default tree of joins;
+    if gather_joins:
+      # Removed: with all small joins on one rank, that rank both receives subtree results from a peer and is sent small
+      # tensors by the same peer in the opposite order; torch's eagerly initialised NCCL group serialises a rank's
+      # point-to-point operations on one stream, so the two ranks wait on each other (observed at 8 GPUs).  A plan whose
+      # point-to-point operations are issued in one global order on every rank would be safe; the tree plan below is (a rank
+      # only sends after it has received everything it needs).
+      raise NotImplementedError("gather_joins deadlocks with serialised NCCL point-to-point operations; use the tree plan")
+    # (gather_joins: every step on small operands on one rank (single hop) instead of the default tree of joins — see above;)
     # early_recv: receives posted before the first contraction (the NCCL receive kernels then sit on the GPU while it
     # computes) instead of right before the join; join_graphs: runs of steps above the cut replayed as CUDA graphs
     self.early_recv, self.join_graphs = early_recv, join_graphs
