@@ -386,6 +386,11 @@ class ShardedNetwork:
     # computes) instead of right before the join; join_graphs: runs of steps above the cut replayed as CUDA graphs
     self.early_recv, self.join_graphs = early_recv, join_graphs
     self.owner, self.transfers, self.info = partition_tree(n, path, flops, world, tensor_bytes=tensor_bytes if gather_joins else None)
+    if world > 1 and not schedule_completes(n, ssa, self.owner, self.transfers, world):
+      # e.g. 3, 5 or 6 ranks on the benchmark tree: three ranks each start with a large send to the next one.  Every rank
+      # reaches the same verdict from the same integers, so all of them raise instead of some of them hanging in NCCL.
+      raise NotImplementedError("this partition makes ranks wait on each other when point-to-point operations complete in issue "
+                                "order (serialised NCCL p2p); supported on this network: 2, 4, 7, 8 ranks")
     self.producer = {o: i for i, (_, _, o) in enumerate(ssa)}
     self.roots, self.pure = local_subtrees(n, ssa, self.owner, rank)
     self.code = T.dtype_code(dtype)
@@ -507,3 +512,51 @@ class ShardedNetwork:
     root_rank = self.owner[-1] if self.ssa else 0
     res = vals.get(self.ssa[-1][2]) if (self.ssa and rank == root_rank) else None
     return res, root_rank
+
+
+def p2p_issue_order(n_inputs, ssa, owner, transfers, rank):
+  """The order in which `ShardedNetwork.run` (late receives) hands point-to-point operations of `rank` to NCCL:
+  sends of local subtree results, then every receive (by producer step), then the sends of results computed above the cut, in
+  step order.  torch's eagerly initialised NCCL group completes a rank's operations in this order (one stream), which is what
+  `tests/test_host_logic_r2.py` simulates to show that no two ranks can wait on each other.  -> [("send"|"recv", tensor, peer)]"""
+  producer = {o: i for i, (_, _, o) in enumerate(ssa)}
+  roots, pure = local_subtrees(n_inputs, ssa, owner, rank)
+  outgoing, incoming = {}, []
+  for t, src, dst, _ in transfers:
+    if rank == src:
+      outgoing.setdefault(t, []).append(dst)
+    if rank == dst:
+      incoming.append((producer.get(t, -1), t, src))
+  incoming.sort()
+  ops = []
+  for root in roots:                                  # (dict order = the order ShardedNetwork builds and runs its local graphs)
+    for dst in outgoing.get(root, ()):
+      ops.append(("send", root, dst))
+  for _, t, src in incoming:
+    ops.append(("recv", t, src))
+  for s, (_, _, o) in enumerate(ssa):
+    if owner[s] != rank or s in pure:
+      continue
+    for dst in outgoing.get(o, ()):
+      ops.append(("send", o, dst))
+  return ops
+
+
+def schedule_completes(n_inputs, ssa, owner, transfers, world):
+  """True iff every point-to-point operation of the plan completes when each rank's operations complete strictly in issue
+  order and a send needs its matching receive (the conservative model of torch's eagerly initialised NCCL group with large
+  messages).  Pure integer simulation: every rank evaluates it identically before anything is posted."""
+  queues = [p2p_issue_order(n_inputs, ssa, owner, transfers, r) for r in range(world)]
+  progress = True
+  while progress and any(queues):
+    progress = False
+    for r in range(world):
+      if not queues[r]:
+        continue
+      kind, t, peer = queues[r][0]
+      want = ("recv" if kind == "send" else "send", t, r)
+      if queues[peer] and queues[peer][0] == want:
+        queues[r].pop(0)
+        queues[peer].pop(0)
+        progress = True
+  return not any(queues)
