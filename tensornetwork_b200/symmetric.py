@@ -24,24 +24,18 @@ _CLASS = None
 
 
 def _modulus(charge):
-  """None for U(1), N for Z_N; raises for anything this adapter does not cover."""
-  from tensornetwork.block_sparse import charge as ch  # pylint: disable=import-outside-toplevel
+  """None for U(1), N for Z_N; raises for anything this adapter does not cover.  The reference builds Z_N classes in a factory
+  (`charge.py:549-600`, class name `ModularCharge`) without recording N; the dual of charge 1 reveals it: -1 for U(1), N-1 for Z_N
+  (Z2: 1)."""
   types = charge.charge_types
   if len(types) != 1:
     raise NotImplementedError("symmetric_b200 supports one symmetry per leg, got a product of {}".format(len(types)))
-  t = types[0]
-  if t is ch.U1Charge:
+  d = int(np.asarray(types[0].dual_charges(np.array([1], dtype=np.int16))).ravel()[0])
+  if d == -1:
     return None
-  if t is ch.Z2Charge:
-    return 2
-  n = getattr(t, "n", None) or getattr(t, "N", None)
-  if n is None:
-    name = getattr(t, "__name__", "")
-    if name.startswith("Z") and name.endswith("Charge") and name[1:-6].isdigit():
-      n = int(name[1:-6])
-  if n is None:
-    raise NotImplementedError("symmetric_b200: unsupported charge type {}".format(t))
-  return int(n)
+  if d >= 1:
+    return d + 1
+  raise NotImplementedError("symmetric_b200: unsupported charge type {}".format(types[0]))
 
 
 def _to_device(tensor, be):

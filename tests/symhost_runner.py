@@ -39,4 +39,19 @@ for trial in range(120):
   flat = np.concatenate(m1) if m1 else np.zeros(0, dtype=np.int64)
   assert np.array_equal(q1, q2) and np.array_equal(d1, d2) and np.array_equal(flat, dm.numpy()[:flat.shape[0]]), trial
 print("device maps ok")
+
+# ---- Z_N charges (the reference builds the class in a factory, charge.py:549): Z3 tensordot and svd through the adapter
+from tensornetwork.backends import backend_factory as _bf
+_be, _ref = _bf.get_backend("symmetric_b200"), _bf.get_backend("symmetric")
+np.random.seed(7)
+Z3 = tn.ZNCharge(3)
+zl = [tn.Index(Z3.random(d, 0, 2), f) for d, f in zip((5, 6, 4, 7), (False, True, False, True))]
+za = tn.BlockSparseTensor.random(zl, dtype=np.float64)
+zb = tn.BlockSparseTensor.random([zl[3].copy().flip_flow(), zl[2].copy().flip_flow(), zl[0].copy()], dtype=np.float64)
+g, w = _be.tensordot(za, zb, ([2, 3], [1, 0])), _ref.tensordot(za, zb, ([2, 3], [1, 0]))
+assert g.shape == w.shape and np.allclose(g.data, w.data, atol=1e-12), "Z3 tensordot"
+gu, gs, gv, _ = _be.svd(za, 2)
+wu, ws, wv, _ = _ref.svd(za, 2)
+assert np.allclose(gs.data, ws.data, atol=1e-10), "Z3 svd"
+print("Z_N ok")
 print("SYMHOST OK")
