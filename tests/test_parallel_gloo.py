@@ -4,6 +4,7 @@ import os
 import socket
 import subprocess
 import sys
+import pytest
 from tensornetwork_b200 import parallel
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -46,3 +47,29 @@ def test_partition_covers_every_step_and_respects_dependencies():
   assert len(set(owner)) == 4
   for t, src, dst, before in transfers:
     assert src != dst
+
+
+def _run_workers(script, world, extra_env=None):
+  port = str(_free_port())
+  procs = []
+  for r in range(world):
+    env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=port, **(extra_env or {}))
+    procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", script)], env=env,
+                                  stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+  outs = [p.communicate(timeout=300)[0] for p in procs]
+  assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+  return outs
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_network_executor_over_gloo(world):
+  """parallel.ShardedNetwork.run (bench.py's strong_scaling executor) on the world sizes the driver's scaling run uses: result
+  equal to the oracle on the root rank, and the point-to-point operations it issues, in order, equal to the model
+  (`p2p_issue_order`) the deadlock check simulates.  See tests/sharded_worker.py."""
+  outs = _run_workers("sharded_worker.py", world)
+  assert "SHARDED OK world=%d" % world in outs[0]
+
+
+def test_sharded_network_refuses_a_cyclic_plan_on_every_rank():
+  outs = _run_workers("sharded_worker.py", 3, {"SHARDED_EXPECT_REFUSAL": "1"})
+  assert "SHARDED REFUSED world=3" in outs[0]
