@@ -171,7 +171,7 @@ def case_contractors(tn, be, seed=5):
   rng = np.random.default_rng(seed)
   kets = mps_kets(rng, 10, 16)
   out = [H(tn.contractors.greedy(_mps_norm_nodes(tn, be, kets)).tensor)]
-  kets = mps_kets(rng, 4, 4)
+  kets = mps_kets(rng, 3, 4)     # 6 nodes: the stand-in optimal search (numpy's brute force, baseline/refenv.py) is exponential
   out.append(H(tn.contractors.optimal(_mps_norm_nodes(tn, be, kets)).tensor))
   out.append(H(tn.contractors.auto(_mps_norm_nodes(tn, be, kets)).tensor))
   # open network with an output edge order (path_contractors.py:79-97)
